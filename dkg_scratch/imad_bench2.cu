@@ -1,0 +1,140 @@
+// Scratch microbenchmark 2: carry-out cost, constant-bank operands, lazy-carry column accumulation.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+struct P16 { uint32_t v[16]; };
+
+// carry-out only, no chain between MACs: (c2:c1:c0) += a*b, 8 independent triples
+__global__ void v_wide_cout(uint32_t* out, int iters, uint32_t s) {
+  uint32_t c0[8], c1[8], c2[8];
+  uint32_t a = threadIdx.x * 2654435761u + s, b = blockIdx.x * 40503u + 12345u + s;
+  for (int i = 0; i < 8; i++) { c0[i] = a + i; c1[i] = b + i; c2[i] = 0; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
+                     : "+r"(c0[i]), "+r"(c1[i]), "+r"(c2[i]) : "r"(a), "r"(b));
+  }
+  uint32_t r = 0;
+  for (int i = 0; i < 8; i++) r ^= c0[i] ^ c1[i] ^ c2[i];
+  if (r == 0x12345678u) out[0] = r;
+}
+// plain wide with constant-bank multiplier
+__global__ void v_wide_const(uint32_t* out, int iters, uint32_t s, P16 p) {
+  uint64_t acc[8];
+  uint32_t a = threadIdx.x * 2654435761u + s;
+  for (int i = 0; i < 8; i++) acc[i] = (uint64_t)(a + i) << 17;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        acc[i] = (uint64_t)a * p.v[(u + i) & 15] + acc[i];
+    a += (uint32_t)acc[0];
+  }
+  uint64_t r = 0;
+  for (int i = 0; i < 8; i++) r ^= acc[i];
+  if (r == 0x123456789ull) out[0] = (uint32_t)r;
+}
+// plain wide, 16 accumulators, distinct a regs (register-bank realism)
+__global__ void v_wide16(uint32_t* out, int iters, uint32_t s) {
+  uint64_t acc[16]; uint32_t a[8], b[8];
+  for (int i = 0; i < 8; i++) { a[i] = threadIdx.x * 2654435761u + s + i; b[i] = blockIdx.x * 40503u + i * 7 + s; }
+  for (int i = 0; i < 16; i++) acc[i] = (uint64_t)(a[i & 7] + i) << 17;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i + j]) : "r"(a[i]), "r"(b[j]));
+  }
+  uint64_t r = 0;
+  for (int i = 0; i < 16; i++) r ^= acc[i];
+  if (r == 0x123456789ull) out[0] = (uint32_t)r;
+}
+
+// lazy-carry column accumulation block MAC: cols[i+j] += a_i*b_j (no carries), operands reloaded from smem each block
+template <int K, bool CONSTB>
+__global__ void v_lazy(uint32_t* out, int iters, uint32_t s, P16 p) {
+  extern __shared__ uint4 sm[];
+  uint64_t col[2 * K];
+  uint32_t a[K], b[K];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // 8 blocks of K limbs per thread in smem, layout [blk][K/4][thread] of uint4
+  for (int q = 0; q < 8 * (K / 4); q++) sm[q * nt + tid] = make_uint4(tid * 2654435761u + q + s, q * 77u + s, tid + q, s ^ q);
+  __syncthreads();
+  for (int i = 0; i < 2 * K; i++) col[i] = 0;
+  uint32_t mix = 0;
+  for (int it = 0; it < iters; it++) {
+    int ba = it & 7, bb = (it * 3 + 1) & 7;
+#pragma unroll
+    for (int q = 0; q < K / 4; q++) {
+      uint4 va = sm[(ba * (K / 4) + q) * nt + tid];
+      a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
+      if (!CONSTB) {
+        uint4 vb = sm[(bb * (K / 4) + q) * nt + tid];
+        b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++)
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        if (CONSTB) col[i + j] = (uint64_t)(a[i] & 0x7ffffffu) * p.v[j] + col[i + j];
+        else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(col[i + j]) : "r"(a[i]), "r"(b[j]));
+      }
+    // emit low K columns: propagate 27-bit carries, shift window
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < K; i++) { c += col[i]; mix ^= (uint32_t)c & 0x7ffffffu; c >>= 27; }
+    col[K] += c;
+#pragma unroll
+    for (int i = 0; i < K; i++) { col[i] = col[i + K]; col[i + K] = 0; }
+  }
+  uint64_t r = mix;
+  for (int i = 0; i < 2 * K; i++) r ^= col[i];
+  if (r == 0x123456789ull) out[0] = (uint32_t)r;
+}
+
+template <typename F>
+static int run(const char* name, F launch, double macs_per_thread_iter, int iters) {
+  int cfgs[][2] = {{148, 128}, {148, 256}, {148, 384}, {148, 512}, {148, 1024}};
+  for (auto& c : cfgs) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    launch(c[0], c[1], iters / 4);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("%-18s block=%d launch failed\n", name, c[1]); cudaGetLastError(); continue; }
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+      CK(cudaEventRecord(e0));
+      launch(c[0], c[1], iters);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < best) best = ms;
+    }
+    double macs = macs_per_thread_iter * (double)iters * c[0] * c[1];
+    printf("%-18s grid=%4d block=%4d  %8.3f ms  %8.3f Tmac/s  (%.2f mac/clk/SM @1.965GHz)\n", name, c[0], c[1], best,
+           macs / best / 1e9, macs / (best * 1e-3) / 148 / 1.965e9);
+  }
+  return 0;
+}
+
+int main() {
+  uint32_t* out; CK(cudaMalloc(&out, 4096));
+  P16 p; for (int i = 0; i < 16; i++) p.v[i] = 0x9e3779b1u * (i + 1);
+  run("wide_cout", [&](int g, int b, int it) { v_wide_cout<<<g, b>>>(out, it, 1); }, 64, 4000);
+  run("wide_const", [&](int g, int b, int it) { v_wide_const<<<g, b>>>(out, it, 1, p); }, 64, 4000);
+  run("wide16", [&](int g, int b, int it) { v_wide16<<<g, b>>>(out, it, 1); }, 64, 4000);
+  CK(cudaFuncSetAttribute(v_lazy<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(v_lazy<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(v_lazy<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  run("lazy_k16", [&](int g, int b, int it) { v_lazy<16, false><<<g, b, b * 8 * 16 * 4>>>(out, it, 1, p); }, 256, 1000);
+  run("lazy_k16_constb", [&](int g, int b, int it) { v_lazy<16, true><<<g, b, b * 8 * 16 * 4>>>(out, it, 1, p); }, 256, 1000);
+  run("lazy_k8", [&](int g, int b, int it) { v_lazy<8, false><<<g, b, b * 8 * 8 * 4>>>(out, it, 1, p); }, 64, 4000);
+  return 0;
+}
