@@ -1,0 +1,123 @@
+/*
+ * dkg_b200 -- C ABI of the B200 batched modular-exponentiation engine for the data-parallel hot
+ * path of tno.mpc.protocols.distributed_keygen (threshold Paillier).
+ *
+ * The reference has no FFI: its hot path is four Python call sites that call third-party
+ * pow_mod / mod_inv once per element.  Each entry point below replaces one of those per-element
+ * loops by one batched call (reference paths are relative to
+ * src/tno/mpc/protocols/distributed_keygen/ in TNO-MPC/protocols.distributed_keygen v4.2.2):
+ *
+ *   dkg_modexp_batch      <- PaillierSharedKey.partial_decrypt, paillier_shared_key.py:86-93
+ *                            (mod_inv when the exponent is negative :89-91, pow_mod :92), looped
+ *                            by DistributedPaillier._decrypt_sequence_raw, distributed_keygen.py:463-466;
+ *                            also third-party Paillier randomness pow_mod(r, N, N^2)
+ *   dkg_combine_batch     <- PaillierSharedKey.decrypt, paillier_shared_key.py:108-125, looped at
+ *                            distributed_keygen.py:510-515
+ *   dkg_encrypt_batch     <- third-party Paillier.encrypt / randomize: (1 + m N) * r^N mod N^2
+ *                            (g = N + 1, distributed_keygen.py:712)
+ *   dkg_modexp_grouped    <- DistributedPaillier.__biprime_test_v_calculation,
+ *                            distributed_keygen.py:1094,1097, looped by compute_modulus :1313-1329
+ *
+ * Conventions
+ *  - Big integers are arrays of uint32_t limbs, least-significant limb first (the byte order of
+ *    int.to_bytes(4*L, "little") and of the reference's key blobs).  A batch is row-major
+ *    [count][limbs].
+ *  - The caller owns every buffer; nothing is retained after a call returns.
+ *  - Functions return DKG_OK or a DKG_ERR_* code; dkg_last_error() gives the text (thread-local).
+ *  - Per-element status (uint8_t[count]): DKG_STATUS_OK, DKG_STATUS_NOT_INVERTIBLE (base not a
+ *    unit and the exponent is negative: the reference raises ZeroDivisionError from mod_inv),
+ *    DKG_STATUS_NOT_DIVISIBLE (combine: (x-1) % N != 0: the reference raises ValueError,
+ *    paillier_shared_key.py:119-123).  Rows with a non-zero status are zero-filled.
+ *  - Every input value must be < the modulus of its context (the reference's ciphertexts are).
+ *  - A context is bound to one device and one internal stream; calls on one context serialise.
+ *    The *_device variants take device pointers and a cudaStream_t (as void*) and are
+ *    asynchronous with respect to the host; everything else is synchronous.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    DKG_ERR_CUDA.
+ */
+#ifndef DKG_B200_H_
+#define DKG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKG_OK 0
+#define DKG_ERR_INVALID 1       /* bad argument (null pointer, even modulus, size out of range) */
+#define DKG_ERR_CUDA 2          /* CUDA runtime error or no device */
+#define DKG_ERR_UNSUPPORTED 3   /* operand wider than the largest compiled kernel shape */
+#define DKG_ERR_NOMEM 4
+#define DKG_ERR_NOT_IMPLEMENTED 5
+
+#define DKG_STATUS_OK 0
+#define DKG_STATUS_NOT_INVERTIBLE 1
+#define DKG_STATUS_NOT_DIVISIBLE 2
+
+#define DKG_MAX_LIMBS 272 /* widest modulus the compiled kernel shapes cover (8704 bits) */
+
+typedef struct dkg_modexp_ctx dkg_modexp_ctx;
+typedef struct dkg_combine_ctx dkg_combine_ctx;
+
+/* library / device */
+int dkg_version(void);
+const char* dkg_last_error(void);
+int dkg_device_count(int* count);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long dkg_launch_count(void);
+
+/* Register-resident mad.wide.u32 microbenchmark: wide multiply-accumulates per second of the
+ * integer multiplier on `device`, plain (no carry) and carry-chained.  The roofline denominator. */
+int dkg_measure_imad_peak(int device, double* plain_wide_mac_per_s, double* carry_wide_mac_per_s);
+
+/* ---- fixed modulus, fixed signed exponent (per key) --------------------------------------- */
+/* modulus: odd, mod_limbs limbs (<= DKG_MAX_LIMBS); exponent: magnitude in exp_limbs limbs,
+ * sign in exp_negative (0/1).  Precomputes -N^-1, R mod N, R^2 mod N and the window digits. */
+int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs,
+                          const uint32_t* exponent, int exp_limbs, int exp_negative,
+                          dkg_modexp_ctx** out);
+void dkg_modexp_ctx_destroy(dkg_modexp_ctx* ctx);
+/* info[0]=K, [1]=M, [2]=padded limbs, [3]=window bits, [4]=windows, [5]=exponent bits,
+ * [6]=warps per CTA, [7]=CTAs */
+int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[8]);
+
+/* out[i] = bases[i] ^ (+-exponent) mod modulus; rows of mod_limbs limbs.  Host buffers. */
+int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, uint8_t* status,
+                     size_t count);
+/* Same with device buffers on `stream` (cudaStream_t); returns after enqueueing. */
+int dkg_modexp_batch_device(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
+                            uint8_t* d_status, size_t count, void* stream);
+
+/* ---- share combination ---------------------------------------------------------------------- */
+/* n: the Paillier modulus N (n_limbs limbs); theta_inv: theta^-1 mod N (n_limbs limbs);
+ * shares: d+1, the number of partial decryptions multiplied together. */
+int dkg_combine_ctx_create(int device, const uint32_t* n, int n_limbs, const uint32_t* theta_inv,
+                           int shares, dkg_combine_ctx** out);
+void dkg_combine_ctx_destroy(dkg_combine_ctx* ctx);
+/* partials: [shares][count][n2_limbs] with n2_limbs = limbs of N^2 (dkg_combine_n2_limbs);
+ * out: [count][n_limbs]; status[count]. */
+int dkg_combine_n2_limbs(const dkg_combine_ctx* ctx);
+int dkg_combine_batch(dkg_combine_ctx* ctx, const uint32_t* partials, uint32_t* out,
+                      uint8_t* status, size_t count);
+int dkg_combine_batch_device(dkg_combine_ctx* ctx, const uint32_t* d_partials, uint32_t* d_out,
+                             uint8_t* d_status, size_t count, void* stream);
+
+/* ---- encryption: (1 + m N) * r^N mod N^2 ---------------------------------------------------- */
+/* ctx: a modexp context created with modulus = N^2 and exponent = N.  r: [count][n_limbs],
+ * m: [count][n_limbs] or NULL (randomness r^N only); out: [count][n2_limbs]. */
+int dkg_encrypt_batch(dkg_modexp_ctx* ctx, const uint32_t* n, int n_limbs, const uint32_t* r,
+                      const uint32_t* m, uint32_t* out, size_t count);
+
+/* ---- grouped modexp: per-group modulus and exponent (biprimality test) ----------------------- */
+/* moduli: [groups][limbs] (odd); exps: [groups][exp_limbs]; bases: [groups][per_group][limbs];
+ * out: same shape as bases.  Montgomery constants are derived on the device per group. */
+int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint32_t* exps, int exp_limbs,
+                       const uint32_t* bases, uint32_t* out, size_t groups, int per_group,
+                       int limbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKG_B200_H_ */

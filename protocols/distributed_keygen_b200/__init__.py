@@ -1,0 +1,14 @@
+"""
+B200-native batched modular-exponentiation engine for the data-parallel hot path of
+``tno.mpc.protocols.distributed_keygen`` (threshold Paillier): partial decryption, share
+combination, encryption randomness and the biprimality-test exponentiations.
+
+The arithmetic runs in hand-written sm_100a CUDA kernels behind a C ABI
+(``include/dkg_b200.h`` -> ``libdkg_b200.so``); this package is the Python host side that mirrors
+the reference's interface for that path.  Importing it requires the built shared library; there is
+no CPU fallback.
+"""
+from . import _native  # noqa: F401  (fails loudly if the CUDA engine is not built)
+from .engine import ModexpContext, launch_count  # noqa: F401
+
+__all__ = ["ModexpContext", "launch_count"]

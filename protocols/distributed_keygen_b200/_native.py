@@ -1,0 +1,87 @@
+"""
+ctypes binding of ``libdkg_b200.so`` (C ABI declared in ``include/dkg_b200.h``).
+
+There is deliberately no CPU fallback: if the shared library has not been built
+(``python -c "import __graft_entry__ as g; g.build()"``) importing this module raises, and every
+compute entry point returns ``DKG_ERR_CUDA`` when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdkg_b200.so")
+
+DKG_OK = 0
+DKG_ERR_INVALID = 1
+DKG_ERR_CUDA = 2
+DKG_ERR_UNSUPPORTED = 3
+DKG_ERR_NOMEM = 4
+DKG_ERR_NOT_IMPLEMENTED = 5
+
+STATUS_OK = 0
+STATUS_NOT_INVERTIBLE = 1
+STATUS_NOT_DIVISIBLE = 2
+
+# every symbol include/dkg_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "dkg_version", "dkg_last_error", "dkg_device_count", "dkg_launch_count",
+    "dkg_measure_imad_peak",
+    "dkg_modexp_ctx_create", "dkg_modexp_ctx_destroy", "dkg_modexp_ctx_info",
+    "dkg_modexp_batch", "dkg_modexp_batch_device",
+    "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
+    "dkg_combine_batch", "dkg_combine_batch_device",
+    "dkg_encrypt_batch", "dkg_modexp_grouped",
+]
+
+
+class DkgError(RuntimeError):
+    def __init__(self, code: int, message: str) -> None:
+        super().__init__(f"dkg_b200 error {code}: {message}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA engine has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c_u32p, c_u8p, c_void = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
+    lib.dkg_version.restype = ctypes.c_int
+    lib.dkg_last_error.restype = ctypes.c_char_p
+    lib.dkg_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    lib.dkg_launch_count.restype = ctypes.c_ulonglong
+    lib.dkg_measure_imad_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.dkg_modexp_ctx_create.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void)]
+    lib.dkg_modexp_ctx_destroy.argtypes = [c_void]
+    lib.dkg_modexp_ctx_destroy.restype = None
+    lib.dkg_modexp_ctx_info.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 8)]
+    lib.dkg_modexp_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
+    lib.dkg_modexp_batch_device.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t, c_void]
+    lib.dkg_combine_ctx_create.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.POINTER(c_void)]
+    lib.dkg_combine_ctx_destroy.argtypes = [c_void]
+    lib.dkg_combine_ctx_destroy.restype = None
+    lib.dkg_combine_n2_limbs.argtypes = [c_void]
+    lib.dkg_combine_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
+    lib.dkg_combine_batch_device.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t, c_void]
+    lib.dkg_encrypt_batch.argtypes = [c_void, c_u32p, ctypes.c_int, c_u32p, c_u32p, c_u32p, ctypes.c_size_t]
+    lib.dkg_modexp_grouped.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u32p, c_u32p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != DKG_OK:
+        msg = lib.dkg_last_error()
+        raise DkgError(rc, msg.decode() if msg else "")
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    rc = lib.dkg_device_count(ctypes.byref(n))
+    return n.value if rc == DKG_OK else 0

@@ -1,0 +1,317 @@
+// C ABI of the engine (include/dkg_b200.h): contexts, constant derivation, kernel dispatch.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/dkg_b200.h"
+#include "dkg_host_bigint.h"
+#include "dkg_modexp.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(DKG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+  } while (0)
+
+// ---- kernel shapes -----------------------------------------------------------------------------
+// (K, M): block size and block count; padded width K*M limbs.  Sorted by padded width.
+struct Shape { int K, M; };
+constexpr Shape kShapes[] = {
+    {4, 1},  {4, 2},  {4, 3},   {8, 2},   {6, 3},   {12, 2},  {16, 2},  {12, 3},  {16, 3},
+    {16, 4}, {22, 3}, {16, 5},  {16, 6},  {16, 8},  {12, 11}, {16, 9},  {16, 12}, {16, 16},
+    {20, 13}, {16, 17},
+};
+
+using KernelFn = void (*)(const dkg::ModexpParams);
+
+template <int K, int M>
+KernelFn kernel_of() { return dkg::modexp_fixed_kernel<K, M>; }
+
+KernelFn lookup_kernel(int K, int M) {
+#define DKG_CASE(K_, M_) if (K == K_ && M == M_) return kernel_of<K_, M_>();
+  DKG_CASE(4, 1) DKG_CASE(4, 2) DKG_CASE(4, 3) DKG_CASE(8, 2) DKG_CASE(6, 3) DKG_CASE(12, 2)
+  DKG_CASE(16, 2) DKG_CASE(12, 3) DKG_CASE(16, 3) DKG_CASE(16, 4) DKG_CASE(22, 3) DKG_CASE(16, 5)
+  DKG_CASE(16, 6) DKG_CASE(16, 8) DKG_CASE(12, 11) DKG_CASE(16, 9) DKG_CASE(16, 12)
+  DKG_CASE(16, 16) DKG_CASE(20, 13) DKG_CASE(16, 17)
+#undef DKG_CASE
+  return nullptr;
+}
+
+bool pick_shape(int limbs, Shape* out) {
+  for (const Shape& s : kShapes)
+    if (s.K * s.M >= limbs) { *out = s; return true; }
+  return false;
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+struct DeviceState {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t* scratch = nullptr;
+  size_t scratch_words = 0;
+  unsigned int* counter = nullptr;
+};
+std::mutex g_dev_mu;
+DeviceState g_devs[16];
+
+int device_state(int device, DeviceState** out) {
+  if (device < 0 || device >= 16) return fail(DKG_ERR_INVALID, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceState& d = g_devs[device];
+  if (d.device < 0) {
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device >= count) return fail(DKG_ERR_CUDA, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&d.counter, sizeof(unsigned int)));
+    d.device = device;
+  }
+  *out = &d;
+  return DKG_OK;
+}
+
+int ensure_scratch(DeviceState* d, size_t words) {
+  if (d->scratch_words >= words) return DKG_OK;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if (d->scratch) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(d->scratch));
+    d->scratch = nullptr;
+    d->scratch_words = 0;
+  }
+  cudaError_t e = cudaMalloc(&d->scratch, words * sizeof(uint32_t));
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("scratch cudaMalloc: ") + cudaGetErrorString(e));
+  d->scratch_words = words;
+  return DKG_OK;
+}
+
+}  // namespace
+
+struct dkg_modexp_ctx {
+  DeviceState* dev = nullptr;
+  int limbs = 0;  // caller-visible row width
+  Shape shape{};
+  int Lp = 0;
+  int wbits = 1, ndigits = 0, ebits = 0;
+  int negative = 0;
+  uint32_t n0inv = 0;
+  int warps = 1, ctas = 1;
+  size_t smem = 0;
+  size_t scratch_per_warp = 0;
+  KernelFn kernel = nullptr;
+  uint32_t* d_consts = nullptr;
+  uint8_t* d_digits = nullptr;
+};
+
+namespace {
+
+int choose_window(int ebits) {
+  int best = 1;
+  long best_cost = -1;
+  for (int w = 1; w <= 6; ++w) {
+    long cost = ((1L << w) - 2) + (ebits + w - 1) / w;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
+  }
+  return best;
+}
+
+int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
+                  const uint32_t* d_final_mul, size_t count, cudaStream_t stream) {
+  if (count == 0) return DKG_OK;
+  DeviceState* d = ctx->dev;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const unsigned long long ngroups = (count + 31) / 32;
+  const int total_warps = ctx->ctas * ctx->warps;
+  int ctas = ctx->ctas;
+  if (ngroups < (unsigned long long)total_warps) ctas = (int)((ngroups + ctx->warps - 1) / ctx->warps);
+  int rc = ensure_scratch(d, (size_t)total_warps * ctx->scratch_per_warp);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
+  dkg::ModexpParams p{};
+  p.bases = d_bases; p.out = d_out; p.status = d_status; p.count = count; p.in_limbs = ctx->limbs;
+  p.consts = ctx->d_consts; p.digits = ctx->d_digits; p.ndigits = ctx->ndigits; p.wbits = ctx->wbits;
+  p.negative = ctx->negative; p.n0inv = ctx->n0inv; p.scratch = d->scratch;
+  p.scratch_per_warp = ctx->scratch_per_warp; p.counter = d->counter; p.final_mul = d_final_mul;
+  ctx->kernel<<<ctas, ctx->warps * 32, ctx->smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return DKG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dkg_version(void) { return 100; }
+
+const char* dkg_last_error(void) { return g_err.c_str(); }
+
+int dkg_device_count(int* count) {
+  if (!count) return fail(DKG_ERR_INVALID, "null count");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) { *count = 0; return fail(DKG_ERR_CUDA, cudaGetErrorString(e)); }
+  return DKG_OK;
+}
+
+unsigned long long dkg_launch_count(void) { return g_launches.load(); }
+
+int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, const uint32_t* exponent,
+                          int exp_limbs, int exp_negative, dkg_modexp_ctx** out) {
+  if (!modulus || !out || mod_limbs <= 0 || exp_limbs < 0 || (exp_limbs > 0 && !exponent))
+    return fail(DKG_ERR_INVALID, "null/empty argument");
+  if (mod_limbs > DKG_MAX_LIMBS) return fail(DKG_ERR_UNSUPPORTED, "modulus wider than DKG_MAX_LIMBS");
+  if ((modulus[0] & 1u) == 0) return fail(DKG_ERR_INVALID, "modulus must be odd");
+  Shape shape;
+  if (!pick_shape(mod_limbs, &shape)) return fail(DKG_ERR_UNSUPPORTED, "no kernel shape for this width");
+  DeviceState* dev = nullptr;
+  int rc = device_state(device, &dev);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+
+  auto* ctx = new dkg_modexp_ctx();
+  ctx->dev = dev;
+  ctx->limbs = mod_limbs;
+  ctx->shape = shape;
+  ctx->Lp = shape.K * shape.M;
+  ctx->negative = exp_negative ? 1 : 0;
+  ctx->kernel = lookup_kernel(shape.K, shape.M);
+  if (!ctx->kernel) { delete ctx; return fail(DKG_ERR_UNSUPPORTED, "kernel shape not compiled"); }
+
+  const int Lp = ctx->Lp, K = shape.K;
+  dkg_host::Limbs n(Lp, 0);
+  for (int i = 0; i < mod_limbs; ++i) n[i] = modulus[i];
+  dkg_host::Limbs ninv = dkg_host::neg_inv_block(n, K);
+  dkg_host::Limbs one_r = dkg_host::pow2_mod((size_t)32 * Lp, n);
+  dkg_host::Limbs r2 = dkg_host::pow2_mod((size_t)64 * Lp, n);
+  ctx->n0inv = ninv[0];
+
+  std::vector<uint32_t> consts;
+  consts.insert(consts.end(), n.begin(), n.end());
+  consts.insert(consts.end(), ninv.begin(), ninv.end());
+  consts.insert(consts.end(), r2.begin(), r2.end());
+  consts.insert(consts.end(), one_r.begin(), one_r.end());
+
+  // window digits
+  ctx->ebits = exp_limbs ? dkg_host::bit_length(exponent, exp_limbs) : 0;
+  ctx->wbits = choose_window(ctx->ebits);
+  ctx->ndigits = (ctx->ebits + ctx->wbits - 1) / ctx->wbits;
+  std::vector<uint8_t> digits(std::max(ctx->ndigits, 1), 0);
+  for (int t = 0; t < ctx->ndigits; ++t) {
+    const int lowbit = ctx->wbits * (ctx->ndigits - 1 - t);
+    unsigned dgt = 0;
+    for (int b = 0; b < ctx->wbits; ++b) {
+      const int bit = lowbit + b;
+      if (bit < ctx->ebits && ((exponent[bit / 32] >> (bit % 32)) & 1u)) dgt |= 1u << b;
+    }
+    digits[t] = (uint8_t)dgt;
+  }
+
+  // launch geometry: one CTA per SM, as many warps as shared memory allows (<= 8)
+  const size_t uni = (((size_t)(Lp + K) * 4 + 15) / 16) * 16;
+  const size_t per_warp = (size_t)2 * Lp * 32 * 4;
+  int warps = (int)std::min<size_t>(8, (kMaxDynSmem - uni) / per_warp);
+  if (warps < 1) { delete ctx; return fail(DKG_ERR_UNSUPPORTED, "operand too wide for shared memory"); }
+  ctx->warps = warps;
+  ctx->ctas = dev->sm_count;
+  ctx->smem = uni + per_warp * warps;
+  const size_t tsize = ((size_t)1 << ctx->wbits) - 1;
+  ctx->scratch_per_warp = std::max<size_t>(tsize, 2) * (size_t)Lp * 32;
+
+  cudaError_t e = cudaFuncSetAttribute((const void*)ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
+  if (e != cudaSuccess) { delete ctx; return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+  e = cudaMalloc(&ctx->d_consts, consts.size() * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_digits, digits.size());
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_digits, digits.data(), digits.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    dkg_modexp_ctx_destroy(ctx);
+    return fail(DKG_ERR_CUDA, std::string("context upload: ") + cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return DKG_OK;
+}
+
+void dkg_modexp_ctx_destroy(dkg_modexp_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->dev) cudaSetDevice(ctx->dev->device);
+  if (ctx->d_consts) cudaFree(ctx->d_consts);
+  if (ctx->d_digits) cudaFree(ctx->d_digits);
+  delete ctx;
+}
+
+int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[8]) {
+  if (!ctx || !info) return fail(DKG_ERR_INVALID, "null argument");
+  info[0] = ctx->shape.K; info[1] = ctx->shape.M; info[2] = ctx->Lp; info[3] = ctx->wbits;
+  info[4] = ctx->ndigits; info[5] = ctx->ebits; info[6] = ctx->warps; info[7] = ctx->ctas;
+  return DKG_OK;
+}
+
+int dkg_modexp_batch_device(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
+                            uint8_t* d_status, size_t count, void* stream) {
+  if (!ctx || (count && (!d_bases || !d_out))) return fail(DKG_ERR_INVALID, "null argument");
+  return launch_modexp(ctx, d_bases, d_out, d_status, nullptr, count, (cudaStream_t)stream);
+}
+
+int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, uint8_t* status,
+                     size_t count) {
+  if (!ctx || (count && (!bases || !out))) return fail(DKG_ERR_INVALID, "null argument");
+  if (count == 0) return DKG_OK;
+  DeviceState* d = ctx->dev;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const size_t bytes = count * (size_t)ctx->limbs * 4;
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  uint8_t* d_st = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_st, count);
+  int rc = DKG_OK;
+  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("batch cudaMalloc: ") + cudaGetErrorString(e));
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(d_in, bases, bytes, cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == DKG_OK) rc = launch_modexp(ctx, d_in, d_out, d_st, nullptr, count, d->stream);
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_st, count, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("modexp batch: ") + cudaGetErrorString(e));
+  }
+  if (d_in) cudaFree(d_in);
+  if (d_out) cudaFree(d_out);
+  if (d_st) cudaFree(d_st);
+  return rc;
+}
+
+// ---- not yet implemented entry points ------------------------------------------------------------
+int dkg_measure_imad_peak(int, double*, double*) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+int dkg_combine_ctx_create(int, const uint32_t*, int, const uint32_t*, int, dkg_combine_ctx**) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+void dkg_combine_ctx_destroy(dkg_combine_ctx*) {}
+int dkg_combine_n2_limbs(const dkg_combine_ctx*) { return 0; }
+int dkg_combine_batch(dkg_combine_ctx*, const uint32_t*, uint32_t*, uint8_t*, size_t) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+int dkg_combine_batch_device(dkg_combine_ctx*, const uint32_t*, uint32_t*, uint8_t*, size_t, void*) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+int dkg_encrypt_batch(dkg_modexp_ctx*, const uint32_t*, int, const uint32_t*, const uint32_t*, uint32_t*, size_t) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+int dkg_modexp_grouped(int, const uint32_t*, const uint32_t*, int, const uint32_t*, uint32_t*, size_t, int, int) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Carry-chain primitives for 32-bit-limb big-integer arithmetic on sm_100a.
+//
+// On the device every helper is one or two PTX instructions on the CC.CF carry flag; ptxas fuses
+// each mad.lo.cc/madc.hi.cc pair into ONE `IMAD.WIDE.U32[.X] Rd, P, Ra, Rb, Rc, P` (64-bit
+// multiply-accumulate with predicate carry-in/out) and renames CC.CF onto P0..P6, so several
+// chains are in flight at once (checked with cuobjdump; see DESIGN.md "SASS evidence").
+// `asm volatile` keeps the statements of one chain in program order.
+//
+// The host versions (plain C on a thread-local carry bit) exist only so that the *same* templates
+// in dkg_mont.cuh can be unit-tested on a machine without a GPU (tests/host/); they are never
+// compiled into the product library's compute path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DKG_HD __host__ __device__ __forceinline__
+#else
+#define DKG_HD inline
+#endif
+
+namespace dkg {
+
+#if defined(__CUDA_ARCH__)
+
+// {hi,lo} += a*b                      (starts a chain: carry-out only)
+DKG_HD void mad_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// {hi,lo} += a*b + CF                 (continues a chain)
+DKG_HD void madc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// lo += lo32(a*b)                     (no flags)
+DKG_HD void mad_lo(uint32_t& lo, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
+}
+// lo += lo32(a*b) + CF                (ends a chain, carry-out dropped)
+DKG_HD void madc_lo(uint32_t& lo, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
+}
+DKG_HD void add_cc(uint32_t& x, uint32_t y) { asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x) : "r"(y)); }
+DKG_HD void addc_cc(uint32_t& x, uint32_t y) { asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x) : "r"(y)); }
+DKG_HD void addc(uint32_t& x, uint32_t y) { asm volatile("addc.u32 %0, %0, %1;" : "+r"(x) : "r"(y)); }
+
+#else  // host emulation (unit tests only)
+
+namespace detail {
+inline uint32_t& cf() {
+  static thread_local uint32_t flag = 0;
+  return flag;
+}
+inline void add3(uint32_t& x, uint32_t y, uint32_t cin, bool set) {
+  uint64_t s = (uint64_t)x + y + cin;
+  x = (uint32_t)s;
+  if (set) cf() = (uint32_t)(s >> 32);
+}
+}  // namespace detail
+
+DKG_HD void mad_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  uint64_t p = (uint64_t)a * b;
+  detail::add3(lo, (uint32_t)p, 0, true);
+  detail::add3(hi, (uint32_t)(p >> 32), detail::cf(), true);
+}
+DKG_HD void madc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  uint64_t p = (uint64_t)a * b;
+  detail::add3(lo, (uint32_t)p, detail::cf(), true);
+  detail::add3(hi, (uint32_t)(p >> 32), detail::cf(), true);
+}
+DKG_HD void mad_lo(uint32_t& lo, uint32_t a, uint32_t b) { lo += a * b; }
+DKG_HD void madc_lo(uint32_t& lo, uint32_t a, uint32_t b) { lo += a * b + detail::cf(); }
+DKG_HD void add_cc(uint32_t& x, uint32_t y) { detail::add3(x, y, 0, true); }
+DKG_HD void addc_cc(uint32_t& x, uint32_t y) { detail::add3(x, y, detail::cf(), true); }
+DKG_HD void addc(uint32_t& x, uint32_t y) { detail::add3(x, y, detail::cf(), false); }
+
+#endif
+
+}  // namespace dkg

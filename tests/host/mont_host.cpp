@@ -1,0 +1,42 @@
+// Host build of the SAME block-Montgomery templates the CUDA kernels instantiate
+// (protocols/distributed_keygen_b200/csrc/dkg_mont.cuh), with the PTX carry primitives replaced by their C
+// emulation.  Test scaffolding only: lets `pytest -m "not gpu"` check the index logic, bounds and
+// carry handling of the kernels' arithmetic against Python big integers without a GPU.
+#include <cstring>
+#include "dkg_mont.cuh"
+
+namespace {
+template <int K, int M>
+struct HostIO {
+  uint32_t* X; const uint32_t* Y; uint32_t* Q; const uint32_t* N; const uint32_t* NI;
+  void load_x(int i, uint32_t (&r)[K]) { std::memcpy(r, X + i * K, K * 4); }
+  void load_y(int j, uint32_t (&r)[K]) { std::memcpy(r, Y + j * K, K * 4); }
+  void load_q(int i, uint32_t (&r)[K]) { std::memcpy(r, Q + i * K, K * 4); }
+  void load_n(int j, uint32_t (&r)[K]) { std::memcpy(r, N + j * K, K * 4); }
+  void load_ninv(uint32_t (&r)[K]) { std::memcpy(r, NI, K * 4); }
+  void store_q(int i, const uint32_t (&r)[K]) { std::memcpy(Q + i * K, r, K * 4); }
+  void store_x(int i, const uint32_t (&r)[K]) { std::memcpy(X + i * K, r, K * 4); }
+};
+
+template <int K, int M>
+int run(int mode, uint32_t* x, const uint32_t* y, const uint32_t* n, const uint32_t* ninv, int canon) {
+  uint32_t q[K * M];
+  std::memset(q, 0, sizeof(q));
+  HostIO<K, M> io{x, y, q, n, ninv};
+  if (mode == 0) dkg::mont_mul<K, M, dkg::MONT_MUL>(io);
+  else if (mode == 1) { io.Y = x; dkg::mont_mul<K, M, dkg::MONT_MUL>(io); }
+  else dkg::mont_mul<K, M, dkg::MONT_REDC>(io);
+  if (canon) dkg::canonicalize<K, M>(io, canon);
+  return 0;
+}
+}  // namespace
+
+#define CASE(K_, M_) if (K == K_ && M == M_) return run<K_, M_>(mode, x, y, n, ninv, canon);
+
+// mode 0: x <- x*y/R mod n; 1: x <- x*x/R (y aliased to x, in place); 2: x <- x/R.
+extern "C" int host_mont(int K, int M, int mode, uint32_t* x, const uint32_t* y, const uint32_t* n,
+                         const uint32_t* ninv, int canon) {
+  CASE(2, 1) CASE(2, 3) CASE(4, 2) CASE(4, 5) CASE(6, 3) CASE(8, 4) CASE(12, 3) CASE(16, 2)
+  CASE(16, 8) CASE(12, 11) CASE(22, 3) CASE(22, 6) CASE(16, 16)
+  return -1;
+}
