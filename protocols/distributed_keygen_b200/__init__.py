@@ -9,6 +9,7 @@ the reference's interface for that path.  Importing it requires the built shared
 no CPU fallback.
 """
 from . import _native  # noqa: F401  (fails loudly if the CUDA engine is not built)
-from .engine import ModexpContext, launch_count  # noqa: F401
+from .engine import CombineContext, ModexpContext, launch_count  # noqa: F401
+from .paillier_shared_key import IntegerShares, PaillierSharedKey  # noqa: F401
 
-__all__ = ["ModexpContext", "launch_count"]
+__all__ = ["CombineContext", "ModexpContext", "PaillierSharedKey", "IntegerShares", "launch_count"]

@@ -11,7 +11,8 @@
 
 #include "../../../include/dkg_b200.h"
 #include "dkg_host_bigint.h"
-#include "dkg_modexp.cuh"
+#include "dkg_modexp_params.h"
+#include "dkg_combine.cuh"
 
 namespace {
 
@@ -40,17 +41,20 @@ constexpr Shape kShapes[] = {
 };
 
 using KernelFn = void (*)(const dkg::ModexpParams);
-
-template <int K, int M>
-KernelFn kernel_of() { return dkg::modexp_fixed_kernel<K, M>; }
+}  // namespace
+namespace dkg {
+// one per dkg_kernels_<n>.cu
+KernelFn lookup_kernel_group0(int, int); KernelFn lookup_kernel_group1(int, int);
+KernelFn lookup_kernel_group2(int, int); KernelFn lookup_kernel_group3(int, int);
+KernelFn lookup_kernel_group4(int, int); KernelFn lookup_kernel_group5(int, int);
+}  // namespace dkg
+namespace {
 
 KernelFn lookup_kernel(int K, int M) {
-#define DKG_CASE(K_, M_) if (K == K_ && M == M_) return kernel_of<K_, M_>();
-  DKG_CASE(4, 1) DKG_CASE(4, 2) DKG_CASE(4, 3) DKG_CASE(8, 2) DKG_CASE(6, 3) DKG_CASE(12, 2)
-  DKG_CASE(16, 2) DKG_CASE(12, 3) DKG_CASE(16, 3) DKG_CASE(16, 4) DKG_CASE(22, 3) DKG_CASE(16, 5)
-  DKG_CASE(16, 6) DKG_CASE(16, 8) DKG_CASE(12, 11) DKG_CASE(16, 9) DKG_CASE(16, 12)
-  DKG_CASE(16, 16) DKG_CASE(20, 13) DKG_CASE(16, 17)
-#undef DKG_CASE
+  KernelFn (*groups[])(int, int) = {dkg::lookup_kernel_group0, dkg::lookup_kernel_group1, dkg::lookup_kernel_group2,
+                                    dkg::lookup_kernel_group3, dkg::lookup_kernel_group4, dkg::lookup_kernel_group5};
+  for (auto g : groups)
+    if (KernelFn f = g(K, M)) return f;
   return nullptr;
 }
 
@@ -305,13 +309,135 @@ int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, 
 }
 
 // ---- not yet implemented entry points ------------------------------------------------------------
-int dkg_measure_imad_peak(int, double*, double*) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
-int dkg_combine_ctx_create(int, const uint32_t*, int, const uint32_t*, int, dkg_combine_ctx**) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
-void dkg_combine_ctx_destroy(dkg_combine_ctx*) {}
-int dkg_combine_n2_limbs(const dkg_combine_ctx*) { return 0; }
-int dkg_combine_batch(dkg_combine_ctx*, const uint32_t*, uint32_t*, uint8_t*, size_t) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
-int dkg_combine_batch_device(dkg_combine_ctx*, const uint32_t*, uint32_t*, uint8_t*, size_t, void*) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
 int dkg_encrypt_batch(dkg_modexp_ctx*, const uint32_t*, int, const uint32_t*, const uint32_t*, uint32_t*, size_t) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
 int dkg_modexp_grouped(int, const uint32_t*, const uint32_t*, int, const uint32_t*, uint32_t*, size_t, int, int) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
+
+}  // extern "C"
+
+// ---- share combination ---------------------------------------------------------------------------
+struct dkg_combine_ctx {
+  DeviceState* dev = nullptr;
+  int ln = 0, l2 = 0, shares = 0;
+  uint32_t n2_0inv = 0, n_0inv = 0;
+  uint32_t* d_consts = nullptr;
+};
+
+namespace {
+int launch_combine(dkg_combine_ctx* ctx, const uint32_t* d_partials, uint32_t* d_out, uint8_t* d_status,
+                   size_t count, cudaStream_t stream) {
+  if (count == 0) return DKG_OK;
+  CUDA_TRY(cudaSetDevice(ctx->dev->device));
+  dkg::CombineParams p{};
+  p.partials = d_partials; p.out = d_out; p.status = d_status; p.count = count; p.shares = ctx->shares;
+  p.l2 = ctx->l2; p.ln = ctx->ln; p.consts = ctx->d_consts; p.n2_0inv = ctx->n2_0inv; p.n_0inv = ctx->n_0inv;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((count + threads - 1) / threads);
+  dkg::combine_kernel<<<blocks, threads, 0, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return DKG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dkg_combine_ctx_create(int device, const uint32_t* n, int n_limbs, const uint32_t* theta_inv, int shares,
+                           dkg_combine_ctx** out) {
+  if (!n || !theta_inv || !out || n_limbs <= 0 || shares < 1) return fail(DKG_ERR_INVALID, "null/empty argument");
+  if ((n[0] & 1u) == 0) return fail(DKG_ERR_INVALID, "modulus must be odd");
+  int ln = n_limbs;
+  while (ln > 1 && n[ln - 1] == 0) --ln;
+  if (ln > dkg::kCombineMaxL - 1) return fail(DKG_ERR_UNSUPPORTED, "N wider than the combine kernel supports");
+  DeviceState* dev = nullptr;
+  int rc = device_state(device, &dev);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  // N^2 by schoolbook
+  dkg_host::Limbs nn(n, n + ln), n2(2 * ln, 0);
+  for (int i = 0; i < ln; ++i) {
+    uint64_t carry = 0;
+    for (int j = 0; j < ln; ++j) {
+      uint64_t t = (uint64_t)nn[i] * nn[j] + n2[i + j] + carry;
+      n2[i + j] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    n2[i + ln] = (uint32_t)carry;
+  }
+  int l2 = 2 * ln;
+  while (l2 > 1 && n2[l2 - 1] == 0) --l2;
+  n2.resize(l2);
+  dkg_host::Limbs rpow = dkg_host::pow2_mod((size_t)32 * l2 * shares, n2);
+  dkg_host::Limbs ninvneg = dkg_host::neg_inv_block(nn, ln);
+  dkg_host::Limbs ninvpos(ln);
+  {
+    uint64_t carry = 1;
+    for (int i = 0; i < ln; ++i) { uint64_t t = (uint64_t)(~ninvneg[i]) + carry; ninvpos[i] = (uint32_t)t; carry = t >> 32; }
+  }
+  dkg_host::Limbs th(ln, 0);
+  for (int i = 0; i < ln && i < n_limbs; ++i) th[i] = theta_inv[i];
+  if (!dkg_host::geq(nn, th) || th == nn) return fail(DKG_ERR_INVALID, "theta_inv must be < N");
+  dkg_host::Limbs thr = dkg_host::mulmod_slow(th, dkg_host::pow2_mod((size_t)32 * ln, nn), nn);
+
+  auto* ctx = new dkg_combine_ctx();
+  ctx->dev = dev; ctx->ln = ln; ctx->l2 = l2; ctx->shares = shares;
+  ctx->n2_0inv = dkg_host::neg_inv_block(n2, 1)[0];
+  ctx->n_0inv = ninvneg[0];
+  std::vector<uint32_t> consts;
+  consts.insert(consts.end(), n2.begin(), n2.end());
+  consts.insert(consts.end(), rpow.begin(), rpow.end());
+  consts.insert(consts.end(), nn.begin(), nn.end());
+  consts.insert(consts.end(), ninvpos.begin(), ninvpos.end());
+  consts.insert(consts.end(), thr.begin(), thr.end());
+  cudaError_t e = cudaMalloc(&ctx->d_consts, consts.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { dkg_combine_ctx_destroy(ctx); return fail(DKG_ERR_CUDA, std::string("combine ctx: ") + cudaGetErrorString(e)); }
+  *out = ctx;
+  return DKG_OK;
+}
+
+void dkg_combine_ctx_destroy(dkg_combine_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->dev) cudaSetDevice(ctx->dev->device);
+  if (ctx->d_consts) cudaFree(ctx->d_consts);
+  delete ctx;
+}
+
+int dkg_combine_n2_limbs(const dkg_combine_ctx* ctx) { return ctx ? ctx->l2 : 0; }
+
+int dkg_combine_batch_device(dkg_combine_ctx* ctx, const uint32_t* d_partials, uint32_t* d_out, uint8_t* d_status,
+                             size_t count, void* stream) {
+  if (!ctx || (count && (!d_partials || !d_out))) return fail(DKG_ERR_INVALID, "null argument");
+  return launch_combine(ctx, d_partials, d_out, d_status, count, (cudaStream_t)stream);
+}
+
+int dkg_combine_batch(dkg_combine_ctx* ctx, const uint32_t* partials, uint32_t* out, uint8_t* status, size_t count) {
+  if (!ctx || (count && (!partials || !out))) return fail(DKG_ERR_INVALID, "null argument");
+  if (count == 0) return DKG_OK;
+  DeviceState* d = ctx->dev;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const size_t in_bytes = (size_t)ctx->shares * count * ctx->l2 * 4, out_bytes = count * (size_t)ctx->ln * 4;
+  uint32_t *d_in = nullptr, *d_out = nullptr;
+  uint8_t* d_st = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, in_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_st, count);
+  int rc = DKG_OK;
+  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("combine cudaMalloc: ") + cudaGetErrorString(e));
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(d_in, partials, in_bytes, cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == DKG_OK) rc = launch_combine(ctx, d_in, d_out, d_st, count, d->stream);
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_st, count, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("combine batch: ") + cudaGetErrorString(e));
+  }
+  if (d_in) cudaFree(d_in);
+  if (d_out) cudaFree(d_out);
+  if (d_st) cudaFree(d_st);
+  return rc;
+}
 
 }  // extern "C"

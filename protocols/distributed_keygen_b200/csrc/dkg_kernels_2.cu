@@ -1,0 +1,4 @@
+// Kernel instantiations, group 2 (split across translation units so they compile in parallel).
+#define DKG_GROUP 2
+#define DKG_GROUP_SHAPES(X) X(16,16) X(12,3) X(16,3)
+#include "dkg_kernels.inc"

@@ -1,0 +1,4 @@
+// Kernel instantiations, group 5 (split across translation units so they compile in parallel).
+#define DKG_GROUP 5
+#define DKG_GROUP_SHAPES(X) X(16,9) X(16,12)
+#include "dkg_kernels.inc"

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "dkg_mont.cuh"
+#include "dkg_modexp_params.h"
 
 namespace dkg {
 
@@ -75,25 +76,6 @@ struct WarpIO {
   }
 };
 
-struct ModexpParams {
-  const uint32_t* bases;   // [count][in_limbs]
-  uint32_t* out;           // [count][in_limbs]
-  uint8_t* status;         // [count] or null
-  unsigned long long count;
-  int in_limbs;
-  // device constants: N[Lp] | NINV[K] | R2[Lp] | ONER[Lp]   (Lp = K*M)
-  const uint32_t* consts;
-  const uint8_t* digits;   // window digits, most significant first
-  int ndigits;
-  int wbits;
-  int negative;            // invert the base first
-  uint32_t n0inv;          // -N^-1 mod 2^32
-  uint32_t* scratch;       // per-warp table scratch
-  unsigned long long scratch_per_warp;  // in uint32
-  unsigned int* counter;   // work-group ticket
-  // optional per-element plain multiplier applied at the end (encryption: 1 + m N), or null
-  const uint32_t* final_mul;  // [count][in_limbs]
-};
 
 // limb l of a lane-private big integer stored vector-major in shared memory (base = lane's vector 0)
 template <int VW>
@@ -184,6 +166,14 @@ __device__ uint32_t mod_inverse_lane(uint32_t* U, uint32_t* Vv, const uint32_t* 
   return bad ? 1u : 0u;
 }
 
+// Out-of-line instances of the Montgomery product: the kernel body calls these (three function
+// bodies per shape: square, multiply-by-global-operand, reduce) instead of inlining seven copies,
+// which keeps the hot loop inside the instruction cache.
+template <int K, int M, int YMODE, int MODE>
+__device__ __noinline__ void mont_call(const WarpIO<K, M, YMODE> io) {
+  mont_mul<K, M, MODE>(io);
+}
+
 template <int K, int M>
 __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams p) {
   using V = typename VecSel<K>::T;
@@ -242,7 +232,7 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
 
     // ---- to Montgomery form: X <- X * R^2 / R ------------------------------------------------
     io_mul.Y = R2g; io_mul.ystride = 1;
-    mont_mul<K, M, MONT_MUL>(io_mul);
+    mont_call<K, M, 1, MONT_MUL>(io_mul);
 
     if (p.ndigits == 0) {
       for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = ONEg[v];
@@ -252,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
       for (int v = 0; v < LV; ++v) tab[(size_t)v * 32 + lane] = Xw[v * 32 + lane];
       for (int d = 2; d <= tsize; ++d) {
         io_mul.Y = tab + lane; io_mul.ystride = 32;
-        mont_mul<K, M, MONT_MUL>(io_mul);
+        mont_call<K, M, 1, MONT_MUL>(io_mul);
         V* dst = tab + (size_t)(d - 1) * LV * 32 + lane;
         for (int v = 0; v < LV; ++v) dst[(size_t)v * 32] = Xw[v * 32 + lane];
       }
@@ -263,11 +253,11 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
         for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = src[(size_t)v * 32];
       }
       for (int t = 1; t < p.ndigits; ++t) {
-        for (int s = 0; s < p.wbits; ++s) mont_mul<K, M, MONT_MUL>(io_sqr);
+        for (int s = 0; s < p.wbits; ++s) mont_call<K, M, 0, MONT_MUL>(io_sqr);
         const int d = p.digits[t];
         if (d == 0) { io_mul.Y = ONEg; io_mul.ystride = 1; }
         else { io_mul.Y = tab + (size_t)(d - 1) * LV * 32 + lane; io_mul.ystride = 32; }
-        mont_mul<K, M, MONT_MUL>(io_mul);
+        mont_call<K, M, 1, MONT_MUL>(io_mul);
       }
     }
 
@@ -285,9 +275,9 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
       }
       __syncwarp();
       io_mul.Y = tab + lane; io_mul.ystride = 32;
-      mont_mul<K, M, MONT_MUL>(io_mul);   // (x R) * y / R = x y
+      mont_call<K, M, 1, MONT_MUL>(io_mul);   // (x R) * y / R = x y
     } else {
-      mont_mul<K, M, MONT_REDC>(io_sqr);
+      mont_call<K, M, 0, MONT_REDC>(io_sqr);
     }
     canonicalize<K, M>(io_sqr, p.final_mul != nullptr ? 2 : 1);
     __syncwarp();

@@ -123,7 +123,7 @@ DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32
 // MONT_REDC: X <- X * R^-1 mod N
 // Result in [0, R); X is overwritten block by block (block c-M is dead when column c starts).
 template <int K, int M, int MODE, class IO>
-DKG_HD void mont_mul(IO& io) {
+DKG_HD void mont_mul(const IO& io) {
   uint32_t T[2 * K + 2];
 #pragma unroll
   for (int i = 0; i < 2 * K + 2; i++) T[i] = 0;
@@ -199,7 +199,7 @@ DKG_HD void mont_mul(IO& io) {
 
 // X >= N ?  (returns 1/0).  Scans all blocks, no early exit.
 template <int K, int M, class IO>
-DKG_HD uint32_t geq_n(IO& io) {
+DKG_HD uint32_t geq_n(const IO& io) {
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {
     uint32_t xb[K], nb[K];
@@ -216,7 +216,7 @@ DKG_HD uint32_t geq_n(IO& io) {
 
 // X <- X - (N & mask)
 template <int K, int M, class IO>
-DKG_HD void sub_n_masked(IO& io, uint32_t mask) {
+DKG_HD void sub_n_masked(const IO& io, uint32_t mask) {
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {
     uint32_t xb[K], nb[K];
@@ -236,7 +236,7 @@ DKG_HD void sub_n_masked(IO& io, uint32_t mask) {
 // After a MONT_REDC the value is <= N, so one conditional subtraction suffices; `rounds` > 1 is
 // for callers that canonicalise a raw [0, R) value with R < 2^rounds * N.
 template <int K, int M, class IO>
-DKG_HD void canonicalize(IO& io, int rounds = 1) {
+DKG_HD void canonicalize(const IO& io, int rounds = 1) {
   for (int r = 0; r < rounds; ++r) {
     const uint32_t ge = geq_n<K, M>(io);
     sub_n_masked<K, M>(io, 0u - ge);

@@ -84,3 +84,56 @@ class ModexpContext:
 
 def launch_count() -> int:
     return int(_native.lib.dkg_launch_count())
+
+
+class CombineContext:
+    """Batched share combination: the arithmetic of ``PaillierSharedKey.decrypt``
+    (``paillier_shared_key.py:108-125`` of the reference) for ``shares`` = degree + 1 partial
+    decryptions per ciphertext."""
+
+    def __init__(self, n: int, theta_inv: int, shares: int, device: int = 0) -> None:
+        if n <= 0 or n % 2 == 0:
+            raise ValueError("n must be a positive odd integer")
+        self.n = n
+        self.shares = shares
+        self.device = device
+        self.n_limbs = limbs_for_bits(n.bit_length())
+        self.n2_limbs = limbs_for_bits((n * n).bit_length())
+        self._n = int_to_limbs(n, self.n_limbs)
+        self._th = int_to_limbs(theta_inv % n, self.n_limbs)
+        handle = ctypes.c_void_p()
+        _native.check(
+            _native.lib.dkg_combine_ctx_create(
+                device, self._n.ctypes.data, self.n_limbs, self._th.ctypes.data, shares, ctypes.byref(handle)
+            )
+        )
+        self._h = handle
+        assert _native.lib.dkg_combine_n2_limbs(self._h) == self.n2_limbs
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _native.lib.dkg_combine_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def combine_limbs(self, partials: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        """partials: uint32 [shares, count, n2_limbs].  Returns (plaintexts [count, n_limbs],
+        status [count]) with status 2 where (x - 1) is not divisible by N."""
+        partials = np.ascontiguousarray(partials, dtype=np.uint32)
+        if partials.ndim != 3 or partials.shape[0] != self.shares or partials.shape[2] != self.n2_limbs:
+            raise ValueError(f"partials must have shape [{self.shares}, count, {self.n2_limbs}]")
+        count = partials.shape[1]
+        out = np.zeros((count, self.n_limbs), dtype=np.uint32)
+        status = np.zeros(count, dtype=np.uint8)
+        _native.check(
+            _native.lib.dkg_combine_batch(self._h, partials.ctypes.data, out.ctypes.data, status.ctypes.data, count)
+        )
+        return out, status
+
+    def combine_device(self, d_partials: int, d_out: int, d_status: int, count: int, stream: int) -> None:
+        _native.check(_native.lib.dkg_combine_batch_device(self._h, d_partials, d_out, d_status, count, stream))

@@ -9,13 +9,13 @@ namespace {
 template <int K, int M>
 struct HostIO {
   uint32_t* X; const uint32_t* Y; uint32_t* Q; const uint32_t* N; const uint32_t* NI;
-  void load_x(int i, uint32_t (&r)[K]) { std::memcpy(r, X + i * K, K * 4); }
-  void load_y(int j, uint32_t (&r)[K]) { std::memcpy(r, Y + j * K, K * 4); }
-  void load_q(int i, uint32_t (&r)[K]) { std::memcpy(r, Q + i * K, K * 4); }
-  void load_n(int j, uint32_t (&r)[K]) { std::memcpy(r, N + j * K, K * 4); }
-  void load_ninv(uint32_t (&r)[K]) { std::memcpy(r, NI, K * 4); }
-  void store_q(int i, const uint32_t (&r)[K]) { std::memcpy(Q + i * K, r, K * 4); }
-  void store_x(int i, const uint32_t (&r)[K]) { std::memcpy(X + i * K, r, K * 4); }
+  void load_x(int i, uint32_t (&r)[K]) const { std::memcpy(r, X + i * K, K * 4); }
+  void load_y(int j, uint32_t (&r)[K]) const { std::memcpy(r, Y + j * K, K * 4); }
+  void load_q(int i, uint32_t (&r)[K]) const { std::memcpy(r, Q + i * K, K * 4); }
+  void load_n(int j, uint32_t (&r)[K]) const { std::memcpy(r, N + j * K, K * 4); }
+  void load_ninv(uint32_t (&r)[K]) const { std::memcpy(r, NI, K * 4); }
+  void store_q(int i, const uint32_t (&r)[K]) const { std::memcpy(Q + i * K, r, K * 4); }
+  void store_x(int i, const uint32_t (&r)[K]) const { std::memcpy(X + i * K, r, K * 4); }
 };
 
 template <int K, int M>
