@@ -1,6 +1,7 @@
 // C ABI of the engine (include/dkg_b200.h): contexts, constant derivation, kernel dispatch.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -123,6 +124,7 @@ struct dkg_modexp_ctx {
   int warps = 1, ctas = 1;
   size_t smem = 0;
   size_t scratch_per_warp = 0;
+  size_t scratch_q_offset = 0;
   KernelFn kernel = nullptr;
   uint32_t* d_consts = nullptr;
   uint8_t* d_digits = nullptr;
@@ -131,6 +133,10 @@ struct dkg_modexp_ctx {
 namespace {
 
 int choose_window(int ebits) {
+  if (const char* f = getenv("DKG_FORCE_WINDOW")) {  // tuning/debug knob
+    int w = atoi(f);
+    if (w >= 1 && w <= 6) return w;
+  }
   int best = 1;
   long best_cost = -1;
   for (int w = 1; w <= 6; ++w) {
@@ -156,7 +162,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
   p.bases = d_bases; p.out = d_out; p.status = d_status; p.count = count; p.in_limbs = ctx->limbs;
   p.consts = ctx->d_consts; p.digits = ctx->d_digits; p.ndigits = ctx->ndigits; p.wbits = ctx->wbits;
   p.negative = ctx->negative; p.n0inv = ctx->n0inv; p.scratch = d->scratch;
-  p.scratch_per_warp = ctx->scratch_per_warp; p.counter = d->counter; p.final_mul = d_final_mul;
+  p.scratch_per_warp = ctx->scratch_per_warp; p.scratch_q_offset = ctx->scratch_q_offset; p.counter = d->counter; p.final_mul = d_final_mul;
   ctx->kernel<<<ctas, ctx->warps * 32, ctx->smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -233,14 +239,16 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
 
   // launch geometry: one CTA per SM, as many warps as shared memory allows (<= 8)
   const size_t uni = (((size_t)(Lp + K) * 4 + 15) / 16) * 16;
-  const size_t per_warp = (size_t)2 * Lp * 32 * 4;
-  int warps = (int)std::min<size_t>(8, (kMaxDynSmem - uni) / per_warp);
+  const size_t per_warp = (size_t)Lp * 32 * 4;  // X only: the quotient blocks live in global scratch
+  int warps = (int)std::min<size_t>(DKG_MAX_THREADS / 32, (kMaxDynSmem - uni) / per_warp);
   if (warps < 1) { delete ctx; return fail(DKG_ERR_UNSUPPORTED, "operand too wide for shared memory"); }
   ctx->warps = warps;
   ctx->ctas = dev->sm_count;
   ctx->smem = uni + per_warp * warps;
   const size_t tsize = ((size_t)1 << ctx->wbits) - 1;
-  ctx->scratch_per_warp = std::max<size_t>(tsize, 2) * (size_t)Lp * 32;
+  // per-warp scratch: window table (also the workspace of the modular inverse: 4 arrays), then Q
+  ctx->scratch_q_offset = std::max<size_t>(tsize, 4) * (size_t)Lp * 32;
+  ctx->scratch_per_warp = ctx->scratch_q_offset + (size_t)Lp * 32;
 
   cudaError_t e = cudaFuncSetAttribute((const void*)ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
   if (e != cudaSuccess) { delete ctx; return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }

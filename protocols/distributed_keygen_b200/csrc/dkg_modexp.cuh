@@ -28,51 +28,86 @@ __device__ __forceinline__ void unpack(const uint2& v, uint32_t* r) { r[0] = v.x
 __device__ __forceinline__ void pack(uint4& v, const uint32_t* r) { v = make_uint4(r[0], r[1], r[2], r[3]); }
 __device__ __forceinline__ void pack(uint2& v, const uint32_t* r) { v = make_uint2(r[0], r[1]); }
 
-// IO policy of dkg::mont_mul for one thread of a warp.  X/Q point at this lane's vector 0.
-// YMODE 0: Y aliases X (squaring); 1: Y is in global memory at Y[v * ystride].
-template <int K, int M, int YMODE>
+// explicit shared-space accesses (32-bit shared addresses): the IO object crosses a noinline call,
+// where the compiler would otherwise lose the address space and emit generic LD/ST
+__device__ __forceinline__ void lds_vec(uint4& v, uint32_t saddr) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void lds_vec(uint2& v, uint32_t saddr) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void sts_vec(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_vec(uint32_t saddr, const uint2& v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(saddr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void ldg_vec(uint4& v, const uint4* p) {
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg_vec(uint4* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_vec(uint2* p, const uint2& v) {
+  asm volatile("st.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void ldg_vec(uint2& v, const uint2* p) {
+  asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+}
+
+// IO policy of dkg::mont_mul for one thread of a warp.
+//  xs      shared-space byte address of this lane's vector 0 of X (consecutive vectors of one
+//          lane are 32 vectors apart); ns/nis: the CTA-uniform modulus and block inverse;
+//  Qg      this lane's Montgomery-quotient blocks in the warp's global scratch (same
+//          vector-major / lane-minor layout; L1/L2 resident, always read through the prefetch);
+//  Y       multiplication operand in global memory at Y[v * ystride].
+template <int K, int M>
 struct WarpIO {
   using V = typename VecSel<K>::T;
   static constexpr int VW = VecSel<K>::VW;
   static constexpr int KV = K / VW;
-  V* X;
-  V* Q;
-  const V* Ns;   // shared, uniform
-  const V* NIs;  // shared, uniform
-  const V* Y;    // global
+  static constexpr uint32_t VB = sizeof(V);
+  uint32_t xs, ns, nis;
+  V* Qg;
+  const V* Y;
   int ystride;
 
   __device__ __forceinline__ void load_x(int i, uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) unpack(X[(i * KV + q) * 32], &r[q * VW]);
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, xs + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_y(int j, uint32_t (&r)[K]) const {
-    if (YMODE == 0) {
-      load_x(j, r);
-    } else {
 #pragma unroll
-      for (int q = 0; q < KV; q++) unpack(Y[(size_t)(j * KV + q) * ystride], &r[q * VW]);
-    }
+    for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Y + (size_t)(j * KV + q) * ystride); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_q(int i, uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) unpack(Q[(i * KV + q) * 32], &r[q * VW]);
+    for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Qg + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
+  }
+  __device__ __forceinline__ void prefetch_x(int i, int v, uint32_t (&r)[K]) const {
+    V t; lds_vec(t, xs + (uint32_t)(i * KV + v) * 32u * VB); unpack(t, &r[v * VW]);
+  }
+  __device__ __forceinline__ void prefetch_y(int j, int v, uint32_t (&r)[K]) const {
+    V t; ldg_vec(t, Y + (size_t)(j * KV + v) * ystride); unpack(t, &r[v * VW]);
+  }
+  __device__ __forceinline__ void prefetch_q(int i, int v, uint32_t (&r)[K]) const {
+    V t; ldg_vec(t, Qg + (size_t)(i * KV + v) * 32); unpack(t, &r[v * VW]);
   }
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) unpack(Ns[j * KV + q], &r[q * VW]);
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, ns + (uint32_t)(j * KV + q) * VB); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_ninv(uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) unpack(NIs[q], &r[q * VW]);
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, nis + (uint32_t)q * VB); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void store_q(int i, const uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) pack(Q[(i * KV + q) * 32], &r[q * VW]);
+    for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); stg_vec(Qg + (size_t)(i * KV + q) * 32, v); }
   }
   __device__ __forceinline__ void store_x(int i, const uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) pack(X[(i * KV + q) * 32], &r[q * VW]);
+    for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); sts_vec(xs + (uint32_t)(i * KV + q) * 32u * VB, v); }
   }
 };
 
@@ -82,33 +117,37 @@ template <int VW>
 __device__ __forceinline__ int sidx(int l) { return (l / VW) * 32 * VW + (l % VW); }
 
 // Modular inverse of the lane's value in X (mod N), binary extended GCD with multi-bit shifts.
-// u (X region) and v (Q region) live in shared memory, the cofactors x1, x2 in the warp's global
-// scratch (stride 32).  Invariants: x1*a = u, x2*a = v (mod N).  Returns 0 if invertible (X <-
-// a^-1 mod N), 1 otherwise (X unspecified).
+// u, v and the cofactors x1, x2 live in the warp's global scratch (limb l of this lane at
+// [l * 32]); Ns is the modulus in shared memory.  Invariants: x1*a = u, x2*a = v (mod N).
+// Returns 0 if invertible (X <- a^-1 mod N), 1 otherwise (X unspecified).
 template <int K, int M>
-__device__ uint32_t mod_inverse_lane(uint32_t* U, uint32_t* Vv, const uint32_t* Ns, uint32_t n0inv,
-                                     uint32_t* g1, uint32_t* g2) {
+__device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n0inv, uint32_t* g) {
   constexpr int VW = VecSel<K>::VW;
   constexpr int Lp = K * M;
+  uint32_t* pu = g;
+  uint32_t* pv = g + Lp * 32;
+  uint32_t* px1 = g + 2 * Lp * 32;
+  uint32_t* px2 = g + 3 * Lp * 32;
   uint32_t nz = 0;
   for (int l = 0; l < Lp; ++l) {
-    Vv[sidx<VW>(l)] = Ns[l];
-    g1[l * 32] = (l == 0) ? 1u : 0u;
-    g2[l * 32] = 0u;
-    nz |= U[sidx<VW>(l)];
+    const uint32_t x = X[sidx<VW>(l)];
+    pu[l * 32] = x;
+    pv[l * 32] = Ns[l];
+    px1[l * 32] = (l == 0) ? 1u : 0u;
+    px2[l * 32] = 0u;
+    nz |= x;
   }
-  uint32_t* pu = U; uint32_t* pv = Vv; uint32_t* px1 = g1; uint32_t* px2 = g2;
   int len = Lp;
   int guard = 64 * Lp + 64;
   while (nz != 0 && guard-- > 0) {
     // 1. make u odd: shift out up to 32 zero bits at a time, dividing x1 by the same power of 2
-    uint32_t u0 = pu[sidx<VW>(0)];
+    uint32_t u0 = pu[0];
     while ((u0 & 1u) == 0) {
       const int tz = u0 ? __ffs(u0) - 1 : 32;
       uint32_t lo = u0;
       for (int l = 0; l < len; ++l) {
-        const uint32_t hi = (l + 1 < len) ? pu[sidx<VW>(l + 1)] : 0u;
-        pu[sidx<VW>(l)] = (uint32_t)((((uint64_t)hi << 32) | lo) >> tz);
+        const uint32_t hi = (l + 1 < len) ? pu[(l + 1) * 32] : 0u;
+        pu[l * 32] = (uint32_t)((((uint64_t)hi << 32) | lo) >> tz);
         lo = hi;
       }
       const uint32_t mask = tz == 32 ? 0xffffffffu : ((1u << tz) - 1u);
@@ -123,12 +162,12 @@ __device__ uint32_t mod_inverse_lane(uint32_t* U, uint32_t* Vv, const uint32_t* 
         prev = cur;
       }
       px1[(Lp - 1) * 32] = (uint32_t)(((carry << 32) | prev) >> tz);
-      u0 = pu[sidx<VW>(0)];
+      u0 = pu[0];
     }
     // 2. order: u >= v
     bool lt = false;
     for (int l = len - 1; l >= 0; --l) {
-      const uint32_t a = pu[sidx<VW>(l)], b = pv[sidx<VW>(l)];
+      const uint32_t a = pu[l * 32], b = pv[l * 32];
       if (a != b) { lt = a < b; break; }
     }
     if (lt) {
@@ -139,8 +178,8 @@ __device__ uint32_t mod_inverse_lane(uint32_t* U, uint32_t* Vv, const uint32_t* 
     uint32_t borrow = 0;
     nz = 0;
     for (int l = 0; l < len; ++l) {
-      const uint64_t d = (uint64_t)pu[sidx<VW>(l)] - pv[sidx<VW>(l)] - borrow;
-      pu[sidx<VW>(l)] = (uint32_t)d;
+      const uint64_t d = (uint64_t)pu[l * 32] - pv[l * 32] - borrow;
+      pu[l * 32] = (uint32_t)d;
       nz |= (uint32_t)d;
       borrow = (uint32_t)(d >> 63);
     }
@@ -156,26 +195,25 @@ __device__ uint32_t mod_inverse_lane(uint32_t* U, uint32_t* Vv, const uint32_t* 
       px1[l * 32] = (uint32_t)t;
       c = t >> 32;
     }
-    while (len > 1 && pu[sidx<VW>(len - 1)] == 0 && pv[sidx<VW>(len - 1)] == 0) --len;
+    while (len > 1 && pu[(len - 1) * 32] == 0 && pv[(len - 1) * 32] == 0) --len;
   }
-  // gcd is in v; invertible iff v == 1
-  uint32_t bad = pv[sidx<VW>(0)] ^ 1u;
-  for (int l = 1; l < Lp; ++l) bad |= pv[sidx<VW>(l)];
-  // the inverse is x2; both u and v are dead now
-  for (int l = 0; l < Lp; ++l) U[sidx<VW>(l)] = px2[l * 32];
+  // gcd is in v; invertible iff v == 1; the inverse is x2
+  uint32_t bad = pv[0] ^ 1u;
+  for (int l = 1; l < Lp; ++l) bad |= pv[l * 32];
+  for (int l = 0; l < Lp; ++l) X[sidx<VW>(l)] = px2[l * 32];
   return bad ? 1u : 0u;
 }
 
 // Out-of-line instances of the Montgomery product: the kernel body calls these (three function
 // bodies per shape: square, multiply-by-global-operand, reduce) instead of inlining seven copies,
 // which keeps the hot loop inside the instruction cache.
-template <int K, int M, int YMODE, int MODE>
-__device__ __noinline__ void mont_call(const WarpIO<K, M, YMODE> io) {
+template <int K, int M, int MODE>
+__device__ __noinline__ void mont_call(const WarpIO<K, M> io) {
   mont_mul<K, M, MODE>(io);
 }
 
 template <int K, int M>
-__global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams p) {
+__global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const ModexpParams p) {
   using V = typename VecSel<K>::T;
   constexpr int VW = VecSel<K>::VW;
   constexpr int Lp = K * M;
@@ -189,8 +227,7 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
   for (int i = threadIdx.x; i < Lp + K; i += blockDim.x) Ns32[i] = p.consts[i];
   __syncthreads();
 
-  V* Xw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * 2 * LV * 32;
-  V* Qw = Xw + LV * 32;
+  V* Xw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * LV * 32;
   uint32_t* Xw32 = reinterpret_cast<uint32_t*>(Xw);
   const V* Ns = reinterpret_cast<const V*>(Ns32);
   const V* NIs = reinterpret_cast<const V*>(Ns32 + Lp);
@@ -200,9 +237,10 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
   const unsigned gwarp = blockIdx.x * nwarps + warp;
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
   V* tab = reinterpret_cast<V*>(scratch32);  // entry d (1-based) at tab[((d-1)*LV + v)*32 + lane]
+  V* Qg = reinterpret_cast<V*>(scratch32 + p.scratch_q_offset);  // quotient blocks, [v*32 + lane]
 
-  WarpIO<K, M, 0> io_sqr{Xw + lane, Qw + lane, Ns, NIs, nullptr, 0};
-  WarpIO<K, M, 1> io_mul{Xw + lane, Qw + lane, Ns, NIs, nullptr, 0};
+  WarpIO<K, M> io{(uint32_t)__cvta_generic_to_shared(Xw + lane), (uint32_t)__cvta_generic_to_shared(Ns),
+                  (uint32_t)__cvta_generic_to_shared(NIs), Qg + lane, nullptr, 0};
 
   const unsigned long long ngroups = (p.count + 31ull) / 32ull;
   for (;;) {
@@ -225,14 +263,13 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
 
     uint32_t st = 0;
     if (p.negative) {
-      st = mod_inverse_lane<K, M>(Xw32 + lane * VW, reinterpret_cast<uint32_t*>(Qw) + lane * VW, Ns32,
-                                  p.n0inv, scratch32 + lane, scratch32 + Lp * 32 + lane);
+      st = mod_inverse_lane<K, M>(Xw32 + lane * VW, Ns32, p.n0inv, scratch32 + lane);
       __syncwarp();
     }
 
     // ---- to Montgomery form: X <- X * R^2 / R ------------------------------------------------
-    io_mul.Y = R2g; io_mul.ystride = 1;
-    mont_call<K, M, 1, MONT_MUL>(io_mul);
+    io.Y = R2g; io.ystride = 1;
+    mont_call<K, M, MONT_MUL>(io);
 
     if (p.ndigits == 0) {
       for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = ONEg[v];
@@ -241,8 +278,8 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
       const int tsize = (1 << p.wbits) - 1;
       for (int v = 0; v < LV; ++v) tab[(size_t)v * 32 + lane] = Xw[v * 32 + lane];
       for (int d = 2; d <= tsize; ++d) {
-        io_mul.Y = tab + lane; io_mul.ystride = 32;
-        mont_call<K, M, 1, MONT_MUL>(io_mul);
+        io.Y = tab + lane; io.ystride = 32;
+        mont_call<K, M, MONT_MUL>(io);
         V* dst = tab + (size_t)(d - 1) * LV * 32 + lane;
         for (int v = 0; v < LV; ++v) dst[(size_t)v * 32] = Xw[v * 32 + lane];
       }
@@ -253,11 +290,11 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
         for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = src[(size_t)v * 32];
       }
       for (int t = 1; t < p.ndigits; ++t) {
-        for (int s = 0; s < p.wbits; ++s) mont_call<K, M, 0, MONT_MUL>(io_sqr);
+        for (int s = 0; s < p.wbits; ++s) mont_call<K, M, MONT_SQR>(io);
         const int d = p.digits[t];
-        if (d == 0) { io_mul.Y = ONEg; io_mul.ystride = 1; }
-        else { io_mul.Y = tab + (size_t)(d - 1) * LV * 32 + lane; io_mul.ystride = 32; }
-        mont_call<K, M, 1, MONT_MUL>(io_mul);
+        if (d == 0) { io.Y = ONEg; io.ystride = 1; }
+        else { io.Y = tab + (size_t)(d - 1) * LV * 32 + lane; io.ystride = 32; }
+        mont_call<K, M, MONT_MUL>(io);
       }
     }
 
@@ -274,12 +311,12 @@ __global__ void __launch_bounds__(256, 1) modexp_fixed_kernel(const ModexpParams
         }
       }
       __syncwarp();
-      io_mul.Y = tab + lane; io_mul.ystride = 32;
-      mont_call<K, M, 1, MONT_MUL>(io_mul);   // (x R) * y / R = x y
+      io.Y = tab + lane; io.ystride = 32;
+      mont_call<K, M, MONT_MUL>(io);   // (x R) * y / R = x y
     } else {
-      mont_call<K, M, 0, MONT_REDC>(io_sqr);
+      mont_call<K, M, MONT_REDC>(io);
     }
-    canonicalize<K, M>(io_sqr, p.final_mul != nullptr ? 2 : 1);
+    canonicalize<K, M>(io, p.final_mul != nullptr ? 2 : 1);
     __syncwarp();
 
     // ---- store rows ---------------------------------------------------------------------------

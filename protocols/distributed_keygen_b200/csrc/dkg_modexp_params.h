@@ -2,6 +2,12 @@
 #pragma once
 #include <stdint.h>
 
+// Threads per CTA the modexp kernels are compiled for (__launch_bounds__): 12 warps = 3 per SM
+// sub-partition, which caps the kernel at 168 registers per thread.
+#ifndef DKG_MAX_THREADS
+#define DKG_MAX_THREADS 384
+#endif
+
 namespace dkg {
 
 struct ModexpParams {
@@ -19,6 +25,7 @@ struct ModexpParams {
   uint32_t n0inv;          // -N^-1 mod 2^32
   uint32_t* scratch;       // per-warp table scratch
   unsigned long long scratch_per_warp;  // in uint32
+  unsigned long long scratch_q_offset;  // offset (uint32) of the quotient-block area inside a warp's scratch
   unsigned int* counter;   // work-group ticket
   // optional per-element plain multiplier applied at the end (encryption: 1 + m N), or null
   const uint32_t* final_mul;  // [count][in_limbs]

@@ -15,58 +15,107 @@
 // at the end of an exponentiation.
 //
 // Work per multiplication: 2*M^2 full block products + M low-half products
-//   = 2*L^2 + L*(K+1)/2 wide multiply-accumulates (the canonical count is 2*L^2 + L).
+//   = 2*L^2 + L*(K+1)/2 wide multiply-accumulates (the canonical count is 2*L^2 + L);
+// per squaring: M(M+1)/2 + M^2 block products + M low-half products (cross products doubled).
 #pragma once
 #include "dkg_prims.cuh"
 
 namespace dkg {
 
-enum MontMode { MONT_MUL = 0, MONT_REDC = 1 };
+enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2 };
 
-// E + (O << 32) = x * y  (fresh product; E, O have 2K+2 limbs, the top ones end up zero)
+// Column accumulator of the block product scan, kept in a carry-save form so that a K x K block
+// multiply-accumulate is nothing but IMAD.WIDE carry chains:
+//   value = E + (O << 32) + sum_k CE[k] << 32(K+2k) + sum_k CO[k] << 32(K+2k+1)
+// E takes the partial products a_i*b_j with i+j even (64-bit aligned at even limbs), O those with
+// i+j odd (aligned at odd limbs); the carry out of every row chain is counted in CE/CO instead of
+// being rippled through the upper limbs, so rows stay independent and nothing is merged inside
+// the inner loop.  `merge` folds everything back into E (once or twice per column).
 template <int K>
-DKG_HD void block_mul(uint32_t (&E)[2 * K + 2], uint32_t (&O)[2 * K + 2], const uint32_t (&x)[K],
-                      const uint32_t (&y)[K]) {
-  static_assert(K % 2 == 0 && K >= 2, "K must be even");
+struct ColAcc {
+  uint32_t E[2 * K + 2];
+  uint32_t O[2 * K - 2];
+  uint32_t CE[K / 2 + 1];
+  uint32_t CO[K / 2];
+};
+
+template <int K>
+DKG_HD void acc_clear_side(ColAcc<K>& a) {
 #pragma unroll
-  for (int i = 0; i < 2 * K + 2; i++) { E[i] = 0; O[i] = 0; }
+  for (int i = 0; i < 2 * K - 2; i++) a.O[i] = 0;
+#pragma unroll
+  for (int i = 0; i < K / 2 + 1; i++) a.CE[i] = 0;
+#pragma unroll
+  for (int i = 0; i < K / 2; i++) a.CO[i] = 0;
+}
+
+// Operand kinds of a block product, also the source selector of the prefetch:
+//   PAIR_XY: x = X_i (shared), y = Y_j (global, multiplication operand / table entry)
+//   PAIR_XX: x = X_i, y = X_j (shared; squaring)
+//   PAIR_NQ: x = N_i (shared, CTA-uniform), y = Q_j (global scratch, written earlier by this thread)
+//   PAIR_QC: the quotient step (x = Q_c fresh in registers, y = N_0)
+enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4 };
+
+struct PairDesc {
+  int kind, xi, yi;
+};
+
+// acc += x * y.  y[j] is dead once row j is done, so while this product runs, y is refilled behind
+// the scan with the y operand of the NEXT block product (kind nk, block ny): vector v is fetched
+// right after the rows that used vector v.  Register-level double buffering: the L2/global latency
+// of Q blocks and table entries hides under the ~1000 multiplier cycles of this product.
+template <int K, class IO>
+DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], const IO& io, int nk, int ny) {
+  static_assert(K % 2 == 0 && K >= 4, "K must be even and >= 4");
+  constexpr int VW = IO::VW;
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    // products x_i*y_j with i+j even land in E at limb i+j; with i+j odd in O at limb i+j-1
     if ((j & 1) == 0) {
-      mad_cc(E[j], E[j + 1], x[0], y[j]);
+      mad_cc(a.E[j], a.E[j + 1], x[0], y[j]);
 #pragma unroll
-      for (int i = 2; i < K; i += 2) madc_cc(E[i + j], E[i + j + 1], x[i], y[j]);
-      addc(E[j + K], 0);
-      mad_cc(O[j], O[j + 1], x[1], y[j]);
+      for (int i = 2; i < K; i += 2) madc_cc(a.E[i + j], a.E[i + j + 1], x[i], y[j]);
+      addc(a.CE[j / 2], 0);  // limb j+K
+      mad_cc(a.O[j], a.O[j + 1], x[1], y[j]);
 #pragma unroll
-      for (int i = 3; i < K; i += 2) madc_cc(O[i + j - 1], O[i + j], x[i], y[j]);
-      addc(O[j + K], 0);
+      for (int i = 3; i < K; i += 2) madc_cc(a.O[i + j - 1], a.O[i + j], x[i], y[j]);
+      addc(a.CO[j / 2], 0);  // O limb j+K
     } else {
-      mad_cc(E[j + 1], E[j + 2], x[1], y[j]);
+      mad_cc(a.E[j + 1], a.E[j + 2], x[1], y[j]);
 #pragma unroll
-      for (int i = 3; i < K; i += 2) madc_cc(E[i + j], E[i + j + 1], x[i], y[j]);
-      addc(E[j + K + 1], 0);
-      mad_cc(O[j - 1], O[j], x[0], y[j]);
+      for (int i = 3; i < K; i += 2) madc_cc(a.E[i + j], a.E[i + j + 1], x[i], y[j]);
+      addc(a.CE[(j + 1) / 2], 0);  // limb j+K+1
+      mad_cc(a.O[j - 1], a.O[j], x[0], y[j]);
 #pragma unroll
-      for (int i = 2; i < K; i += 2) madc_cc(O[i + j - 1], O[i + j], x[i], y[j]);
-      addc(O[j + K - 1], 0);
+      for (int i = 2; i < K; i += 2) madc_cc(a.O[i + j - 1], a.O[i + j], x[i], y[j]);
+      addc(a.CO[(j - 1) / 2], 0);  // O limb j+K-1
+    }
+    if ((j + 1) % VW == 0) {
+      const int v = (j + 1) / VW - 1;
+      if (nk == PAIR_XY) io.prefetch_y(ny, v, y);
+      else if (nk == PAIR_XX) io.prefetch_x(ny, v, y);
+      else if (nk == PAIR_NQ) io.prefetch_q(ny, v, y);
     }
   }
 }
 
-// T += E + (O << 32)
+// fold O, CE, CO into E and clear them
 template <int K>
-DKG_HD void acc_add(uint32_t (&T)[2 * K + 2], const uint32_t (&E)[2 * K + 2],
-                    const uint32_t (&O)[2 * K + 2]) {
-  add_cc(T[0], E[0]);
+DKG_HD void acc_merge(ColAcc<K>& a) {
+  add_cc(a.E[1], a.O[0]);
 #pragma unroll
-  for (int p = 1; p <= 2 * K; p++) addc_cc(T[p], E[p]);
-  addc(T[2 * K + 1], 0);
-  add_cc(T[1], O[0]);
+  for (int p = 1; p < 2 * K - 2; p++) addc_cc(a.E[p + 1], a.O[p]);
+  addc_cc(a.E[2 * K - 1], 0);
+  addc_cc(a.E[2 * K], 0);
+  addc(a.E[2 * K + 1], 0);
+  add_cc(a.E[K], a.CE[0]);
 #pragma unroll
-  for (int p = 1; p <= 2 * K - 1; p++) addc_cc(T[p + 1], O[p]);
-  addc(T[2 * K + 1], 0);
+  for (int k = 0; k < K / 2; k++) {
+    if (k > 0) addc_cc(a.E[K + 2 * k], a.CE[k]);
+    addc_cc(a.E[K + 2 * k + 1], a.CO[k]);
+  }
+  addc_cc(a.E[2 * K], a.CE[K / 2]);
+  addc(a.E[2 * K + 1], 0);
+  acc_clear_side<K>(a);
 }
 
 // r = x[0..K) * y mod 2^(32K)   (x is the low block of a wider array)
@@ -95,105 +144,166 @@ DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32
         mad_cc(O[i0 + j - 1], O[i0 + j], x[i0], y[j]);
 #pragma unroll
         for (int i = i0 + 2; i + j <= K - 3; i += 2) madc_cc(O[i + j - 1], O[i + j], x[i], y[j]);
-        // the element at position K-1 (if this row reaches it) continues the chain, low half only
-        if (((K - 1 - j) & 1) == i0 && K - 1 - j >= 0) madc_lo(O[K - 2], x[K - 1 - j], y[j]);
+        madc_lo(O[K - 2], x[K - 1 - j], y[j]);  // the element at position K-1, low half only
       } else if (i0 + j == K - 1) {
         mad_lo(O[K - 2], x[i0], y[j]);
       }
     }
   }
   r[0] = E[0];
-  if (K == 2) {
-    r[1] = E[1] + O[0];
-  } else {
-    r[1] = E[1];
-    add_cc(r[1], O[0]);
+  r[1] = E[1];
+  add_cc(r[1], O[0]);
 #pragma unroll
-    for (int p = 2; p < K - 1; p++) { r[p] = E[p]; addc_cc(r[p], O[p - 1]); }
-    r[K - 1] = E[K - 1];
-    addc(r[K - 1], O[K - 2]);
-  }
+  for (int p = 2; p < K - 1; p++) { r[p] = E[p]; addc_cc(r[p], O[p - 1]); }
+  r[K - 1] = E[K - 1];
+  addc(r[K - 1], O[K - 2]);
 }
 
-// IO policy (all indices are block indices; r has K limbs):
+// Pair schedule of column c of the block product scan.
+template <int M, int MODE>
+struct ColPlan {
+  int lo, nxy, ncross, nq, total;
+  DKG_HD explicit ColPlan(int c) {
+    lo = c >= M ? c - M + 1 : 0;
+    const int hi = c < M ? c : M - 1;
+    const int span = hi - lo + 1;                     // X_i * Y_{c-i}, i in [lo, hi]
+    // squaring: pairs i < c-i once (doubled afterwards), the middle i == c-i once more
+    ncross = (MODE == MONT_SQR) ? span / 2 : 0;
+    nxy = (MODE == MONT_MUL) ? span : (MODE == MONT_SQR ? ncross + (span & 1) : 0);
+    nq = (c < M ? c - 1 : M - 1) - lo + 1;            // Q_i * N_{c-i}, i in [lo, ..]
+    total = nxy + nq + (c < M ? 1 : 0);               // + the quotient step
+  }
+  // squaring: cross products, (double), middle square, N*Q products, quotient step
+  // multiplication / reduction: N*Q products, X*Y products, quotient step
+  DKG_HD PairDesc at(int c, int t) const {
+    PairDesc d;
+    if (MODE == MONT_SQR) {
+      if (t < nxy) { d.kind = PAIR_XX; d.xi = lo + t; d.yi = c - d.xi; }
+      else if (t < nxy + nq) { d.kind = PAIR_NQ; d.yi = lo + (t - nxy); d.xi = c - d.yi; }
+      else { d.kind = PAIR_QC; d.xi = 0; d.yi = 0; }
+    } else {
+      if (t < nq) { d.kind = PAIR_NQ; d.yi = lo + t; d.xi = c - d.yi; }
+      else if (t < nq + nxy) { d.kind = PAIR_XY; d.xi = lo + (t - nq); d.yi = c - d.xi; }
+      else { d.kind = PAIR_QC; d.xi = 0; d.yi = 0; }
+    }
+    return d;
+  }
+};
+
+// IO policy (all indices are block indices; r has K limbs; VW = limbs per vector):
 //   load_x(i, r)  load_y(j, r)  load_q(i, r)  load_n(j, r)  load_ninv(r)
+//   prefetch_x(i, v, r)  prefetch_y(j, v, r)  prefetch_q(i, v, r)   (vector v of the block)
 //   store_q(i, r) store_x(i, r)
 //
-// MONT_MUL : X <- X * Y * R^-1 mod N   (Y may alias X: squaring)
+// MONT_MUL : X <- X * Y * R^-1 mod N
+// MONT_SQR : X <- X * X * R^-1 mod N   (cross block products computed once and doubled)
 // MONT_REDC: X <- X * R^-1 mod N
 // Result in [0, R); X is overwritten block by block (block c-M is dead when column c starts).
 template <int K, int M, int MODE, class IO>
 DKG_HD void mont_mul(const IO& io) {
-  uint32_t T[2 * K + 2];
+  ColAcc<K> a;
+  uint32_t Tc[K + 2];  // carry-in from the previous column (merged)
 #pragma unroll
-  for (int i = 0; i < 2 * K + 2; i++) T[i] = 0;
+  for (int i = 0; i < K + 2; i++) Tc[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * K + 2; i++) a.E[i] = 0;
+  acc_clear_side<K>(a);
+
+  uint32_t xb[K], yb[K];
+  // operands of the very first block product (everything after it is prefetched)
+  {
+    const PairDesc d = ColPlan<M, MODE>(0).at(0, 0);
+    if (d.kind == PAIR_XY) { io.load_x(d.xi, xb); io.load_y(d.yi, yb); }
+    else if (d.kind == PAIR_XX) { io.load_x(d.xi, xb); io.load_x(d.yi, yb); }
+  }
 
   for (int c = 0; c < 2 * M; ++c) {
-    const int lo = c >= M ? c - M + 1 : 0;
-    const int hi = c < M ? c : M - 1;
-    const int nxy = (MODE == MONT_REDC) ? 0 : (hi - lo + 1);
-    const int nq = (c < M ? c - 1 : M - 1) - lo + 1;
-    const int total = nxy + nq + (c < M ? 1 : 0);
+    const ColPlan<M, MODE> plan(c);
+    const bool defer_carry = (MODE == MONT_SQR) && plan.ncross > 0;
+
+    // seed the accumulator with the carry-in, unless it must not be doubled
+    if (!defer_carry) {
+#pragma unroll
+      for (int p = 0; p < K + 2; p++) a.E[p] = Tc[p];
+    } else {
+#pragma unroll
+      for (int p = 0; p < K + 2; p++) a.E[p] = 0;
+    }
+#pragma unroll
+    for (int p = K + 2; p < 2 * K + 2; p++) a.E[p] = 0;
 
     if (MODE == MONT_REDC && c < M) {
-      uint32_t xb[K];
-      io.load_x(c, xb);
-      add_cc(T[0], xb[0]);
+      uint32_t tb[K];
+      io.load_x(c, tb);
+      add_cc(a.E[0], tb[0]);
 #pragma unroll
-      for (int p = 1; p < K; p++) addc_cc(T[p], xb[p]);
+      for (int p = 1; p < K; p++) addc_cc(a.E[p], tb[p]);
 #pragma unroll
-      for (int p = K; p <= 2 * K; p++) addc_cc(T[p], 0);
-      addc(T[2 * K + 1], 0);
+      for (int p = K; p <= 2 * K; p++) addc_cc(a.E[p], 0);
+      addc(a.E[2 * K + 1], 0);
     }
 
-    for (int t = 0; t < total; ++t) {
-      uint32_t xb[K], yb[K];
-      if (t < nxy) {
-        const int i = lo + t;
-        io.load_x(i, xb);
-        io.load_y(c - i, yb);
-      } else if (t < nxy + nq) {
-        const int i = lo + (t - nxy);
-        io.load_q(i, xb);
-        io.load_n(c - i, yb);
-      } else {
+    for (int t = 0; t < plan.total; ++t) {
+      if (MODE == MONT_SQR && defer_carry && t == plan.ncross) {
+        // all cross products are in: double them, then add the carry-in
+        acc_merge<K>(a);
+#pragma unroll
+        for (int p = 2 * K + 1; p > 0; p--) a.E[p] = (a.E[p] << 1) | (a.E[p - 1] >> 31);
+        a.E[0] <<= 1;
+        add_cc(a.E[0], Tc[0]);
+#pragma unroll
+        for (int p = 1; p < K + 2; p++) addc_cc(a.E[p], Tc[p]);
+#pragma unroll
+        for (int p = K + 2; p <= 2 * K; p++) addc_cc(a.E[p], 0);
+        addc(a.E[2 * K + 1], 0);
+      }
+      if (t == plan.total - 1 && c < M) {
         // quotient block: Q_c = T_low * (-N^-1) mod 2^(32K); Q_c * N_0 then clears T_low
+        acc_merge<K>(a);
         io.load_ninv(yb);
-        block_mul_lo<K>(xb, T, yb);
+        block_mul_lo<K>(xb, a.E, yb);
         io.store_q(c, xb);
         io.load_n(0, yb);
       }
-      uint32_t E[2 * K + 2], O[2 * K + 2];
-      block_mul<K>(E, O, xb, yb);
-      acc_add<K>(T, E, O);
+      // what comes next (possibly in the next column): its y operand is prefetched behind this
+      // block product, its x operand loaded right after
+      PairDesc nx;
+      nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
+      if (t + 1 < plan.total) nx = plan.at(c, t + 1);
+      else if (c + 1 < 2 * M) {
+        const ColPlan<M, MODE> np(c + 1);
+        if (np.total > 0) nx = np.at(c + 1, 0);
+      }
+      block_mac<K>(a, xb, yb, io, nx.kind, nx.yi);
+      if (nx.kind == PAIR_XY || nx.kind == PAIR_XX) io.load_x(nx.xi, xb);
+      else if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
     }
+    acc_merge<K>(a);
 
     if (c >= M) {
       uint32_t ob[K];
 #pragma unroll
-      for (int p = 0; p < K; p++) ob[p] = T[p];
+      for (int p = 0; p < K; p++) ob[p] = a.E[p];
       io.store_x(c - M, ob);
     }
 #pragma unroll
-    for (int p = 0; p < K + 2; p++) T[p] = T[p + K];
-#pragma unroll
-    for (int p = K + 2; p < 2 * K + 2; p++) T[p] = 0;
+    for (int p = 0; p < K + 2; p++) Tc[p] = a.E[p + K];
   }
 
-  // result = T[0]*R + X < R + N: subtract N once iff the carry limb is set
-  const uint32_t mask = 0u - T[0];
+  // result = Tc[0]*R + X < R + N: subtract N once iff the carry limb is set
+  const uint32_t mask = 0u - Tc[0];
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {
-    uint32_t xb[K], nb[K];
-    io.load_x(b, xb);
+    uint32_t tb[K], nb[K];
+    io.load_x(b, tb);
     io.load_n(b, nb);
 #pragma unroll
     for (int p = 0; p < K; p++) {
-      const uint64_t d = (uint64_t)xb[p] - (nb[p] & mask) - borrow;
-      xb[p] = (uint32_t)d;
+      const uint64_t d = (uint64_t)tb[p] - (nb[p] & mask) - borrow;
+      tb[p] = (uint32_t)d;
       borrow = (uint32_t)(d >> 63);
     }
-    io.store_x(b, xb);
+    io.store_x(b, tb);
   }
 }
 

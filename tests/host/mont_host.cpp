@@ -14,6 +14,10 @@ struct HostIO {
   void load_q(int i, uint32_t (&r)[K]) const { std::memcpy(r, Q + i * K, K * 4); }
   void load_n(int j, uint32_t (&r)[K]) const { std::memcpy(r, N + j * K, K * 4); }
   void load_ninv(uint32_t (&r)[K]) const { std::memcpy(r, NI, K * 4); }
+  static constexpr int VW = (K % 4 == 0) ? 4 : 2;
+  void prefetch_y(int j, int v, uint32_t (&r)[K]) const { std::memcpy(r + v * VW, Y + j * K + v * VW, VW * 4); }
+  void prefetch_x(int i, int v, uint32_t (&r)[K]) const { std::memcpy(r + v * VW, X + i * K + v * VW, VW * 4); }
+  void prefetch_q(int i, int v, uint32_t (&r)[K]) const { std::memcpy(r + v * VW, Q + i * K + v * VW, VW * 4); }
   void store_q(int i, const uint32_t (&r)[K]) const { std::memcpy(Q + i * K, r, K * 4); }
   void store_x(int i, const uint32_t (&r)[K]) const { std::memcpy(X + i * K, r, K * 4); }
 };
@@ -25,6 +29,7 @@ int run(int mode, uint32_t* x, const uint32_t* y, const uint32_t* n, const uint3
   HostIO<K, M> io{x, y, q, n, ninv};
   if (mode == 0) dkg::mont_mul<K, M, dkg::MONT_MUL>(io);
   else if (mode == 1) { io.Y = x; dkg::mont_mul<K, M, dkg::MONT_MUL>(io); }
+  else if (mode == 3) dkg::mont_mul<K, M, dkg::MONT_SQR>(io);
   else dkg::mont_mul<K, M, dkg::MONT_REDC>(io);
   if (canon) dkg::canonicalize<K, M>(io, canon);
   return 0;
@@ -33,10 +38,11 @@ int run(int mode, uint32_t* x, const uint32_t* y, const uint32_t* n, const uint3
 
 #define CASE(K_, M_) if (K == K_ && M == M_) return run<K_, M_>(mode, x, y, n, ninv, canon);
 
-// mode 0: x <- x*y/R mod n; 1: x <- x*x/R (y aliased to x, in place); 2: x <- x/R.
+// mode 0: x <- x*y/R mod n; 1: x <- x*x/R (y aliased to x, in place); 2: x <- x/R;
+// 3: x <- x*x/R through the dedicated squaring path.
 extern "C" int host_mont(int K, int M, int mode, uint32_t* x, const uint32_t* y, const uint32_t* n,
                          const uint32_t* ninv, int canon) {
-  CASE(2, 1) CASE(2, 3) CASE(4, 2) CASE(4, 5) CASE(6, 3) CASE(8, 4) CASE(12, 3) CASE(16, 2)
+  CASE(4, 1) CASE(4, 3) CASE(4, 2) CASE(4, 5) CASE(6, 3) CASE(8, 4) CASE(12, 3) CASE(16, 2)
   CASE(16, 8) CASE(12, 11) CASE(22, 3) CASE(22, 6) CASE(16, 16)
   return -1;
 }

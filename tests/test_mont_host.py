@@ -14,7 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "protocols", "distributed_keygen_b200", "csrc")
 
-SHAPES = [(2, 1), (2, 3), (4, 2), (4, 5), (6, 3), (8, 4), (12, 3), (16, 2), (16, 8), (12, 11),
+SHAPES = [(4, 1), (4, 3), (4, 2), (4, 5), (6, 3), (8, 4), (12, 3), (16, 2), (16, 8), (12, 11),
           (22, 3), (22, 6), (16, 16)]
 
 
@@ -59,18 +59,15 @@ def test_mont_mul_host(lib, K, M):
             n = R - 1
         ninv = (-pow(n, -1, W)) % W
         r_inv = pow(R, -1, n)
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             x, y = rng.randrange(R), rng.randrange(R)
             if trial == 1:
                 x = y = R - 1
             if trial == 2:
                 x = 0
-            want = {0: x * y * r_inv, 1: x * x * r_inv, 2: x * r_inv}[mode] % n
+            want = {0: x * y * r_inv, 1: x * x * r_inv, 2: x * r_inv, 3: x * x * r_inv}[mode] % n
             got = _call(lib, K, M, mode, x, y, n, ninv, 0)
             assert got < R and got % n == want, (K, M, mode, trial)
-            # exact: (x*y + q*N)/R, minus N iff it reached R
-            prod = {0: x * y, 1: x * x, 2: x}[mode]
-            q = (prod * ninv) % R if False else None
             # canonical residue after conditional subtraction(s)
             rounds = 1 if mode == 2 else max(1, (R // n).bit_length() + 1)
             if rounds <= 8:
@@ -90,7 +87,7 @@ def test_mont_exponentiation_chain_host(lib):
     acc = R % n
     b_m = base * R % n
     for bit in bin(e)[2:]:
-        acc = _call(lib, K, M, 1, acc, 0, n, ninv, 0)
+        acc = _call(lib, K, M, 3, acc, 0, n, ninv, 0)
         if bit == "1":
             acc = _call(lib, K, M, 0, acc, b_m, n, ninv, 0)
     assert _call(lib, K, M, 2, acc, 0, n, ninv, 1) == pow(base, e, n)
