@@ -181,7 +181,7 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=65536, help="ciphertexts per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="ciphertexts per GPU per step (0 = two full waves of the modexp kernel)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
@@ -215,7 +215,6 @@ def main() -> None:
 
     dk = load_key()
     shares = 2 * dk.t + 1
-    B = args.batch
     keys = {}
     for pid in range(1, shares + 1):
         k = dk.keys[pid]
@@ -225,6 +224,7 @@ def main() -> None:
     comb = keys[1]._combine_ctx()
     L2, Ln = comb.n2_limbs, comb.n_limbs
     info = ctxs[1].info()
+    B = args.batch or 2 * info["ctas"] * info["warps_per_cta"] * 32
     exps = {pid: keys[pid].partial_decrypt_exponent() for pid in keys}
 
     # ---- inputs: real encryptions are not needed for cost, but the result must be checkable:

@@ -48,6 +48,10 @@ namespace dkg {
 KernelFn lookup_kernel_group0(int, int); KernelFn lookup_kernel_group1(int, int);
 KernelFn lookup_kernel_group2(int, int); KernelFn lookup_kernel_group3(int, int);
 KernelFn lookup_kernel_group4(int, int); KernelFn lookup_kernel_group5(int, int);
+using BatchInvFn = void (*)(const BatchInvParams);
+BatchInvFn lookup_batchinv_group0(int, int); BatchInvFn lookup_batchinv_group1(int, int);
+BatchInvFn lookup_batchinv_group2(int, int); BatchInvFn lookup_batchinv_group3(int, int);
+BatchInvFn lookup_batchinv_group4(int, int); BatchInvFn lookup_batchinv_group5(int, int);
 }  // namespace dkg
 namespace {
 
@@ -56,6 +60,15 @@ KernelFn lookup_kernel(int K, int M) {
                                     dkg::lookup_kernel_group3, dkg::lookup_kernel_group4, dkg::lookup_kernel_group5};
   for (auto g : groups)
     if (KernelFn f = g(K, M)) return f;
+  return nullptr;
+}
+
+dkg::BatchInvFn lookup_batchinv(int K, int M) {
+  dkg::BatchInvFn (*groups[])(int, int) = {dkg::lookup_batchinv_group0, dkg::lookup_batchinv_group1,
+                                           dkg::lookup_batchinv_group2, dkg::lookup_batchinv_group3,
+                                           dkg::lookup_batchinv_group4, dkg::lookup_batchinv_group5};
+  for (auto g : groups)
+    if (dkg::BatchInvFn f = g(K, M)) return f;
   return nullptr;
 }
 
@@ -74,6 +87,8 @@ struct DeviceState {
   uint32_t* scratch = nullptr;
   size_t scratch_words = 0;
   unsigned int* counter = nullptr;
+  uint32_t* aux = nullptr;  // batched-inversion buffers
+  size_t aux_words = 0;
 };
 std::mutex g_dev_mu;
 DeviceState g_devs[16];
@@ -111,6 +126,21 @@ int ensure_scratch(DeviceState* d, size_t words) {
   return DKG_OK;
 }
 
+int ensure_aux(DeviceState* d, size_t words) {
+  if (d->aux_words >= words) return DKG_OK;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if (d->aux) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(d->aux));
+    d->aux = nullptr;
+    d->aux_words = 0;
+  }
+  cudaError_t e = cudaMalloc(&d->aux, words * sizeof(uint32_t));
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("aux cudaMalloc: ") + cudaGetErrorString(e));
+  d->aux_words = words;
+  return DKG_OK;
+}
+
 }  // namespace
 
 struct dkg_modexp_ctx {
@@ -126,6 +156,9 @@ struct dkg_modexp_ctx {
   size_t scratch_per_warp = 0;
   size_t scratch_q_offset = 0;
   KernelFn kernel = nullptr;
+  dkg::BatchInvFn inv_kernel = nullptr;
+  int inv_warps = 1;
+  size_t inv_smem = 0;
   uint32_t* d_consts = nullptr;
   uint8_t* d_digits = nullptr;
 };
@@ -159,6 +192,25 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::ModexpParams p{};
+  if (ctx->negative && ctx->inv_kernel != nullptr && ngroups >= 2 && !getenv("DKG_NO_BATCH_INVERSE")) {
+    // Montgomery's trick along chains of ~32 groups: one binary-GCD inversion per chain lane
+    const size_t gwords = (size_t)ctx->Lp * 32;
+    const int nchain = (int)((ngroups + 31) / 32);
+    const int chain_len = (int)((ngroups + nchain - 1) / nchain);
+    const size_t words = 2 * ngroups * gwords + (size_t)nchain * gwords + (size_t)nchain * 32;
+    rc = ensure_aux(d, words);
+    if (rc != DKG_OK) return rc;
+    dkg::BatchInvParams b{};
+    b.bases = d_bases; b.count = count; b.in_limbs = ctx->limbs; b.consts = ctx->d_consts; b.n0inv = ctx->n0inv;
+    b.chain_s = d->aux; b.chain_p = d->aux + ngroups * gwords; b.scratch = d->aux + 2 * ngroups * gwords;
+    b.chain_status = b.scratch + (size_t)nchain * gwords;
+    b.nchain_warps = nchain; b.chain_len = chain_len;
+    const int blocks = (nchain + ctx->inv_warps - 1) / ctx->inv_warps;
+    ctx->inv_kernel<<<blocks, ctx->inv_warps * 32, ctx->inv_smem, stream>>>(b);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    p.inv_mont = b.chain_s; p.chain_status = b.chain_status; p.nchain_warps = nchain;
+  }
   p.bases = d_bases; p.out = d_out; p.status = d_status; p.count = count; p.in_limbs = ctx->limbs;
   p.consts = ctx->d_consts; p.digits = ctx->d_digits; p.ndigits = ctx->ndigits; p.wbits = ctx->wbits;
   p.negative = ctx->negative; p.n0inv = ctx->n0inv; p.scratch = d->scratch;
@@ -214,6 +266,7 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   dkg_host::Limbs ninv = dkg_host::neg_inv_block(n, K);
   dkg_host::Limbs one_r = dkg_host::pow2_mod((size_t)32 * Lp, n);
   dkg_host::Limbs r2 = dkg_host::pow2_mod((size_t)64 * Lp, n);
+  dkg_host::Limbs r3 = dkg_host::pow2_mod((size_t)96 * Lp, n);
   ctx->n0inv = ninv[0];
 
   std::vector<uint32_t> consts;
@@ -221,6 +274,7 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   consts.insert(consts.end(), ninv.begin(), ninv.end());
   consts.insert(consts.end(), r2.begin(), r2.end());
   consts.insert(consts.end(), one_r.begin(), one_r.end());
+  consts.insert(consts.end(), r3.begin(), r3.end());
 
   // window digits
   ctx->ebits = exp_limbs ? dkg_host::bit_length(exponent, exp_limbs) : 0;
@@ -250,6 +304,17 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   ctx->scratch_q_offset = std::max<size_t>(tsize, 4) * (size_t)Lp * 32;
   ctx->scratch_per_warp = ctx->scratch_q_offset + (size_t)Lp * 32;
 
+  ctx->inv_kernel = lookup_batchinv(shape.K, shape.M);
+  {
+    const size_t inv_per_warp = (size_t)6 * Lp * 32 * 4;
+    ctx->inv_warps = (int)std::min<size_t>(2, (kMaxDynSmem - uni) / inv_per_warp);
+    if (ctx->inv_warps < 1) ctx->inv_kernel = nullptr;  // too wide: keep the in-kernel inversion
+    ctx->inv_smem = uni + inv_per_warp * std::max(ctx->inv_warps, 1);
+    if (ctx->inv_kernel) {
+      cudaError_t e2 = cudaFuncSetAttribute((const void*)ctx->inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->inv_smem);
+      if (e2 != cudaSuccess) { delete ctx; return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute(inv): ") + cudaGetErrorString(e2)); }
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute((const void*)ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
   if (e != cudaSuccess) { delete ctx; return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   e = cudaMalloc(&ctx->d_consts, consts.size() * 4);

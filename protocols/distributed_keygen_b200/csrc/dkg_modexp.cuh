@@ -116,26 +116,17 @@ struct WarpIO {
 template <int VW>
 __device__ __forceinline__ int sidx(int l) { return (l / VW) * 32 * VW + (l % VW); }
 
-// Modular inverse of the lane's value in X (mod N), binary extended GCD with multi-bit shifts.
-// u, v and the cofactors x1, x2 live in the warp's global scratch (limb l of this lane at
-// [l * 32]); Ns is the modulus in shared memory.  Invariants: x1*a = u, x2*a = v (mod N).
-// Returns 0 if invertible (X <- a^-1 mod N), 1 otherwise (X unspecified).
-template <int K, int M>
-__device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n0inv, uint32_t* g) {
-  constexpr int VW = VecSel<K>::VW;
-  constexpr int Lp = K * M;
-  uint32_t* pu = g;
-  uint32_t* pv = g + Lp * 32;
-  uint32_t* px1 = g + 2 * Lp * 32;
-  uint32_t* px2 = g + 3 * Lp * 32;
+// Binary extended GCD with multi-bit shifts on four lane-private arrays of `Lp` limbs (limb l at
+// [l * 32] from the given lane-offset pointers; global scratch or shared memory).  On entry u = a,
+// on exit the returned pointer holds a^-1 mod N if *bad == 0.  Invariants: x1*a = u, x2*a = v.
+static __device__ __noinline__ uint32_t* mod_inverse_arrays(uint32_t* pu, uint32_t* pv, uint32_t* px1, uint32_t* px2,
+                                                     const uint32_t* Ns, uint32_t n0inv, int Lp, uint32_t* bad_out) {
   uint32_t nz = 0;
   for (int l = 0; l < Lp; ++l) {
-    const uint32_t x = X[sidx<VW>(l)];
-    pu[l * 32] = x;
     pv[l * 32] = Ns[l];
     px1[l * 32] = (l == 0) ? 1u : 0u;
     px2[l * 32] = 0u;
-    nz |= x;
+    nz |= pu[l * 32];
   }
   int len = Lp;
   int guard = 64 * Lp + 64;
@@ -200,8 +191,22 @@ __device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n
   // gcd is in v; invertible iff v == 1; the inverse is x2
   uint32_t bad = pv[0] ^ 1u;
   for (int l = 1; l < Lp; ++l) bad |= pv[l * 32];
-  for (int l = 0; l < Lp; ++l) X[sidx<VW>(l)] = px2[l * 32];
-  return bad ? 1u : 0u;
+  *bad_out = bad ? 1u : 0u;
+  return px2;
+}
+
+// Modular inverse of the lane's value in X (shared memory, vector-major layout), work arrays in
+// `g` (4 * Lp * 32 words of global scratch or shared memory, lane offset applied).
+// Returns 0 if invertible (X <- a^-1 mod N), 1 otherwise (X unspecified).
+template <int K, int M>
+__device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n0inv, uint32_t* g) {
+  constexpr int VW = VecSel<K>::VW;
+  constexpr int Lp = K * M;
+  for (int l = 0; l < Lp; ++l) g[l * 32] = X[sidx<VW>(l)];
+  uint32_t bad = 0;
+  const uint32_t* r = mod_inverse_arrays(g, g + Lp * 32, g + 2 * Lp * 32, g + 3 * Lp * 32, Ns, n0inv, Lp, &bad);
+  for (int l = 0; l < Lp; ++l) X[sidx<VW>(l)] = r[l * 32];
+  return bad;
 }
 
 // Out-of-line instances of the Montgomery product: the kernel body calls these (three function
@@ -262,14 +267,27 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
     __syncwarp();
 
     uint32_t st = 0;
+    bool in_mont_form = false;
     if (p.negative) {
-      st = mod_inverse_lane<K, M>(Xw32 + lane * VW, Ns32, p.n0inv, scratch32 + lane);
-      __syncwarp();
+      // the batched inversion (dkg_batchinv.cuh) has left c^-1 * R for this group unless its
+      // chain hit a non-invertible element; then every lane of the group inverts on its own
+      uint32_t chain_bad = 1;
+      if (p.inv_mont != nullptr) chain_bad = p.chain_status[(size_t)(g % p.nchain_warps) * 32 + lane];
+      if (__any_sync(0xffffffffu, chain_bad != 0)) {
+        st = mod_inverse_lane<K, M>(Xw32 + lane * VW, Ns32, p.n0inv, scratch32 + lane);
+        __syncwarp();
+      } else {
+        const V* src = reinterpret_cast<const V*>(p.inv_mont + (size_t)g * Lp * 32) + lane;
+        for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = src[(size_t)v * 32];
+        in_mont_form = true;
+      }
     }
 
     // ---- to Montgomery form: X <- X * R^2 / R ------------------------------------------------
-    io.Y = R2g; io.ystride = 1;
-    mont_call<K, M, MONT_MUL>(io);
+    if (!in_mont_form) {
+      io.Y = R2g; io.ystride = 1;
+      mont_call<K, M, MONT_MUL>(io);
+    }
 
     if (p.ndigits == 0) {
       for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = ONEg[v];

@@ -16,7 +16,7 @@ struct ModexpParams {
   uint8_t* status;         // [count] or null
   unsigned long long count;
   int in_limbs;
-  // device constants: N[Lp] | NINV[K] | R2[Lp] | ONER[Lp]   (Lp = K*M)
+  // device constants: N[Lp] | NINV[K] | R2[Lp] | ONER[Lp] | R3[Lp]   (Lp = K*M)
   const uint32_t* consts;
   const uint8_t* digits;   // window digits, most significant first
   int ndigits;
@@ -29,6 +29,28 @@ struct ModexpParams {
   unsigned int* counter;   // work-group ticket
   // optional per-element plain multiplier applied at the end (encryption: 1 + m N), or null
   const uint32_t* final_mul;  // [count][in_limbs]
+  // batched inversion results (negative exponents): c^-1 * R per group in lane layout, and one
+  // flag per chain lane (non-zero: the chain was not invertible as a whole); null = invert in-kernel
+  const uint32_t* inv_mont;       // [groups][Lp * 32]
+  const uint32_t* chain_status;   // [nchain_warps * 32]
+  int nchain_warps;
+};
+
+// Batched modular inversion by Montgomery's trick (dkg_batchinv.cuh): chain warp w owns groups
+// w, w + nchain_warps, w + 2 nchain_warps, ... (a group = 32 consecutive rows; lane l of the warp
+// chains element l of each of its groups).
+struct BatchInvParams {
+  const uint32_t* bases;  // [count][in_limbs]
+  unsigned long long count;
+  int in_limbs;
+  const uint32_t* consts;
+  uint32_t n0inv;
+  uint32_t* chain_s;       // [groups][Lp*32]  c*R, later overwritten with c^-1 * R
+  uint32_t* chain_p;       // [groups][Lp*32]  prefix products
+  uint32_t* chain_status;  // [nchain_warps*32]
+  uint32_t* scratch;       // per-warp quotient-block scratch, [warps][Lp*32]
+  int nchain_warps;
+  int chain_len;           // groups per chain warp (upper bound)
 };
 
 }  // namespace dkg

@@ -62,6 +62,31 @@ def test_negative_exponent_and_status(eng):
         ctx.close()
 
 
+def test_negative_exponent_large_batch_with_non_units(eng):
+    """Batched inversion (Montgomery's trick along chains) with non-invertible elements sprinkled
+    in: only those elements are flagged, every other result is exact."""
+    import math
+
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+
+    rng = random.Random(99)
+    p, q = (1 << 127) - 1, (1 << 89) - 1  # Mersenne primes
+    n = (p * q) ** 2
+    e = -rng.getrandbits(260)
+    ctx = eng.ModexpContext(n, e)
+    bases = [rng.randrange(1, n) for _ in range(3000)]
+    for pos, bad in [(0, 0), (31, p), (32, q * 5), (1500, p * q), (2999, p * p)]:
+        bases[pos] = bad % n
+    out, status = ctx.modexp_limbs(ints_to_limbs(bases, ctx.limbs))
+    vals = limbs_to_ints(out)
+    for i, b in enumerate(bases):
+        if math.gcd(b, n) != 1:
+            assert status[i] == 1 and vals[i] == 0, i
+        else:
+            assert status[i] == 0 and vals[i] == pow(b, e, n), i
+    ctx.close()
+
+
 def test_partial_decrypt_golden_fixture_keys(eng, fixture_vectors):
     """The reference's 24 golden keys: c^(e_i) mod N^2 must equal what the reference's
     PaillierSharedKey.partial_decrypt returned (tests/golden/fixture_vectors.json)."""
