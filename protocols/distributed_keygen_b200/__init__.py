@@ -9,7 +9,11 @@ the reference's interface for that path.  Importing it requires the built shared
 no CPU fallback.
 """
 from . import _native  # noqa: F401  (fails loudly if the CUDA engine is not built)
-from .engine import CombineContext, ModexpContext, launch_count  # noqa: F401
+from .engine import (  # noqa: F401
+    CombineContext, EncryptContext, ModexpContext, launch_count, modexp_grouped, modexp_grouped_limbs,
+)
+from . import distributed_keygen  # noqa: F401
 from .paillier_shared_key import IntegerShares, PaillierSharedKey  # noqa: F401
 
-__all__ = ["CombineContext", "ModexpContext", "PaillierSharedKey", "IntegerShares", "launch_count"]
+__all__ = ["CombineContext", "EncryptContext", "ModexpContext", "PaillierSharedKey", "IntegerShares", "launch_count", "modexp_grouped",
+           "modexp_grouped_limbs", "distributed_keygen"]

@@ -14,6 +14,8 @@
 #include "dkg_host_bigint.h"
 #include "dkg_modexp_params.h"
 #include "dkg_combine.cuh"
+#include "dkg_aux_kernels.cuh"
+#include "dkg_grouped_params_fwd.h"
 
 namespace {
 
@@ -52,6 +54,11 @@ using BatchInvFn = void (*)(const BatchInvParams);
 BatchInvFn lookup_batchinv_group0(int, int); BatchInvFn lookup_batchinv_group1(int, int);
 BatchInvFn lookup_batchinv_group2(int, int); BatchInvFn lookup_batchinv_group3(int, int);
 BatchInvFn lookup_batchinv_group4(int, int); BatchInvFn lookup_batchinv_group5(int, int);
+using GroupedFn = void (*)(const GroupedParams);
+GroupedFn lookup_grouped_group0(int, int); GroupedFn lookup_grouped_group1(int, int);
+GroupedFn lookup_grouped_group2(int, int); GroupedFn lookup_grouped_group3(int, int);
+GroupedFn lookup_grouped_group4(int, int); GroupedFn lookup_grouped_group5(int, int);
+void launch_group_setup(const GroupedParams& p, cudaStream_t stream);
 }  // namespace dkg
 namespace {
 
@@ -382,8 +389,6 @@ int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, 
 }
 
 // ---- not yet implemented entry points ------------------------------------------------------------
-int dkg_encrypt_batch(dkg_modexp_ctx*, const uint32_t*, int, const uint32_t*, const uint32_t*, uint32_t*, size_t) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
-int dkg_modexp_grouped(int, const uint32_t*, const uint32_t*, int, const uint32_t*, uint32_t*, size_t, int, int) { return fail(DKG_ERR_NOT_IMPLEMENTED, "not implemented"); }
 
 }  // extern "C"
 
@@ -514,3 +519,138 @@ int dkg_combine_batch(dkg_combine_ctx* ctx, const uint32_t* partials, uint32_t* 
 }
 
 }  // extern "C"
+
+// ---- encryption: (1 + m N) * r^N mod N^2 ----------------------------------------------------------
+extern "C" int dkg_encrypt_batch(dkg_modexp_ctx* ctx, const uint32_t* n, int n_limbs, const uint32_t* r,
+                                 const uint32_t* m, uint32_t* out, size_t count) {
+  if (!ctx || !n || n_limbs <= 0 || (count && (!r || !out))) return fail(DKG_ERR_INVALID, "null argument");
+  if (n_limbs > ctx->limbs) return fail(DKG_ERR_INVALID, "n wider than the context modulus");
+  if (ctx->negative) return fail(DKG_ERR_INVALID, "encryption needs a context with a positive exponent (N)");
+  if (count == 0) return DKG_OK;
+  DeviceState* d = ctx->dev;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const size_t in_bytes = count * (size_t)n_limbs * 4, out_bytes = count * (size_t)ctx->limbs * 4;
+  uint32_t *d_r = nullptr, *d_m = nullptr, *d_n = nullptr, *d_base = nullptr, *d_fm = nullptr, *d_out = nullptr;
+  int rc = DKG_OK;
+  cudaError_t e = cudaMalloc(&d_r, in_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_base, out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_n, (size_t)n_limbs * 4);
+  if (e == cudaSuccess && m) e = cudaMalloc(&d_m, in_bytes);
+  if (e == cudaSuccess && m) e = cudaMalloc(&d_fm, out_bytes);
+  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("encrypt cudaMalloc: ") + cudaGetErrorString(e));
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(d_r, r, in_bytes, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, n, (size_t)n_limbs * 4, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess && m) e = cudaMemcpyAsync(d_m, m, in_bytes, cudaMemcpyHostToDevice, d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == DKG_OK) {
+    const unsigned blocks = (unsigned)std::min<size_t>((count * ctx->limbs + 255) / 256, 148 * 16);
+    dkg::pad_rows_kernel<<<blocks, 256, 0, d->stream>>>(d_r, n_limbs, d_base, ctx->limbs, count);
+    g_launches.fetch_add(1);
+    if (m) {
+      dkg::one_plus_mn_kernel<<<(unsigned)((count + 127) / 128), 128, 0, d->stream>>>(d_m, d_n, n_limbs, d_fm, ctx->limbs, count);
+      g_launches.fetch_add(1);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == DKG_OK) rc = launch_modexp(ctx, d_base, d_out, nullptr, m ? d_fm : nullptr, count, d->stream);
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("encrypt batch: ") + cudaGetErrorString(e));
+  }
+  for (uint32_t* ptr : {d_r, d_m, d_n, d_base, d_fm, d_out})
+    if (ptr) cudaFree(ptr);
+  return rc;
+}
+
+// ---- grouped modexp (biprimality test batch) -------------------------------------------------------
+namespace {
+dkg::GroupedFn lookup_grouped(int K, int M) {
+  dkg::GroupedFn (*groups[])(int, int) = {dkg::lookup_grouped_group0, dkg::lookup_grouped_group1,
+                                          dkg::lookup_grouped_group2, dkg::lookup_grouped_group3,
+                                          dkg::lookup_grouped_group4, dkg::lookup_grouped_group5};
+  for (auto g : groups)
+    if (dkg::GroupedFn f = g(K, M)) return f;
+  return nullptr;
+}
+}  // namespace
+
+extern "C" int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint32_t* exps, int exp_limbs,
+                                  const uint32_t* bases, uint32_t* out, size_t groups, int per_group, int limbs) {
+  if (!moduli || !exps || !bases || !out || exp_limbs <= 0 || per_group <= 0 || limbs <= 0)
+    return fail(DKG_ERR_INVALID, "null/empty argument");
+  if (groups == 0) return DKG_OK;
+  for (size_t g = 0; g < groups; ++g)
+    if ((moduli[g * (size_t)limbs] & 1u) == 0) return fail(DKG_ERR_INVALID, "every modulus must be odd");
+  Shape shape;
+  dkg::GroupedFn kernel = nullptr;
+  for (const Shape& sh : kShapes)
+    if (sh.K * sh.M >= limbs && (kernel = lookup_grouped(sh.K, sh.M)) != nullptr) { shape = sh; break; }
+  if (!kernel) return fail(DKG_ERR_UNSUPPORTED, "modulus wider than the grouped kernel shapes (132 limbs)");
+  DeviceState* d = nullptr;
+  int rc = device_state(device, &d);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  const int Lp = shape.K * shape.M, K = shape.K;
+  int ebits = 0;
+  for (size_t g = 0; g < groups; ++g) ebits = std::max(ebits, dkg_host::bit_length(exps + g * (size_t)exp_limbs, exp_limbs));
+  const int wbits = choose_window(ebits);
+  const int ndigits = std::max(1, (ebits + wbits - 1) / wbits);
+
+  const size_t count = groups * (size_t)per_group;
+  const size_t vw = (K % 4 == 0) ? 4 : 2;
+  const size_t per_warp_smem = ((size_t)2 * Lp + K) * 32 * 4;
+  (void)vw;
+  int warps = (int)std::min<size_t>(DKG_MAX_THREADS / 32, kMaxDynSmem / per_warp_smem);
+  if (warps < 1) return fail(DKG_ERR_UNSUPPORTED, "operand too wide for shared memory");
+  const size_t smem = per_warp_smem * warps;
+  const size_t tsize = ((size_t)1 << wbits) - 1;
+  const size_t q_off = std::max<size_t>(tsize, 1) * (size_t)Lp * 32;
+  const size_t scratch_per_warp = q_off + (size_t)3 * Lp * 32;  // Q | R2 | ONER in lane layout
+  const unsigned long long nwork = (count + 31) / 32;
+  int ctas = d->sm_count;
+  if (nwork < (unsigned long long)ctas * warps) ctas = (int)((nwork + warps - 1) / warps);
+  rc = ensure_scratch(d, (size_t)d->sm_count * warps * scratch_per_warp);
+  if (rc != DKG_OK) return rc;
+  cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute(grouped): ") + cudaGetErrorString(e));
+
+  uint32_t *d_mod = nullptr, *d_exp = nullptr, *d_bases = nullptr, *d_out = nullptr, *d_gc = nullptr;
+  uint8_t* d_dig = nullptr;
+  const size_t mod_b = groups * (size_t)limbs * 4, exp_b = groups * (size_t)exp_limbs * 4, base_b = count * (size_t)limbs * 4;
+  e = cudaMalloc(&d_mod, mod_b);
+  if (e == cudaSuccess) e = cudaMalloc(&d_exp, exp_b);
+  if (e == cudaSuccess) e = cudaMalloc(&d_bases, base_b);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, base_b);
+  if (e == cudaSuccess) e = cudaMalloc(&d_gc, groups * (size_t)(3 * Lp + K) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_dig, groups * (size_t)ndigits);
+  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("grouped cudaMalloc: ") + cudaGetErrorString(e));
+  if (rc == DKG_OK) {
+    e = cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_exp, exps, exp_b, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases, bases, base_b, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == DKG_OK) {
+    dkg::GroupedParams p{};
+    p.moduli = d_mod; p.exps = d_exp; p.bases = d_bases; p.out = d_out; p.groups = groups;
+    p.per_group = per_group; p.limbs = limbs; p.exp_limbs = exp_limbs; p.K = K; p.Lp = Lp;
+    p.wbits = wbits; p.ndigits = ndigits; p.gconsts = d_gc; p.digits = d_dig; p.scratch = d->scratch;
+    p.scratch_per_warp = scratch_per_warp; p.scratch_q_offset = q_off; p.counter = d->counter;
+    dkg::launch_group_setup(p, d->stream);
+    kernel<<<ctas, warps * 32, smem, d->stream>>>(p);
+    g_launches.fetch_add(2);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, base_b, cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("grouped modexp: ") + cudaGetErrorString(e));
+  }
+  for (void* ptr : {(void*)d_mod, (void*)d_exp, (void*)d_bases, (void*)d_out, (void*)d_gc, (void*)d_dig})
+    if (ptr) cudaFree(ptr);
+  return rc;
+}

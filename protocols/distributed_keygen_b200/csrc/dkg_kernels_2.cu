@@ -1,4 +1,5 @@
 // Kernel instantiations, group 2 (split across translation units so they compile in parallel).
 #define DKG_GROUP 2
 #define DKG_GROUP_SHAPES(X) X(16,16) X(12,3) X(16,3)
+#define DKG_GROUP_GROUPED_SHAPES(X) X(12,3) X(16,3)
 #include "dkg_kernels.inc"

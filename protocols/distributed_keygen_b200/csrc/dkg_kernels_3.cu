@@ -1,4 +1,5 @@
 // Kernel instantiations, group 3 (split across translation units so they compile in parallel).
 #define DKG_GROUP 3
 #define DKG_GROUP_SHAPES(X) X(20,13) X(16,4) X(16,5)
+#define DKG_GROUP_GROUPED_SHAPES(X) X(16,4) X(16,5)
 #include "dkg_kernels.inc"

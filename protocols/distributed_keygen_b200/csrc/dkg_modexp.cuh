@@ -61,12 +61,15 @@ __device__ __forceinline__ void ldg_vec(uint2& v, const uint2* p) {
 //  Qg      this lane's Montgomery-quotient blocks in the warp's global scratch (same
 //          vector-major / lane-minor layout; L1/L2 resident, always read through the prefetch);
 //  Y       multiplication operand in global memory at Y[v * ystride].
-template <int K, int M>
+//  PLN     per-lane modulus: ns/nis then address this lane's copy of N / -N^-1 (32 vectors apart),
+//          as in the grouped kernel where every lane may have its own modulus.
+template <int K, int M, bool PLN = false>
 struct WarpIO {
   using V = typename VecSel<K>::T;
   static constexpr int VW = VecSel<K>::VW;
   static constexpr int KV = K / VW;
   static constexpr uint32_t VB = sizeof(V);
+  static constexpr uint32_t NSTRIDE = PLN ? 32u * VB : VB;
   uint32_t xs, ns, nis;
   V* Qg;
   const V* Y;
@@ -95,11 +98,11 @@ struct WarpIO {
   }
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) { V v; lds_vec(v, ns + (uint32_t)(j * KV + q) * VB); unpack(v, &r[q * VW]); }
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, ns + (uint32_t)(j * KV + q) * NSTRIDE); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_ninv(uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) { V v; lds_vec(v, nis + (uint32_t)q * VB); unpack(v, &r[q * VW]); }
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, nis + (uint32_t)q * NSTRIDE); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void store_q(int i, const uint32_t (&r)[K]) const {
 #pragma unroll
@@ -212,8 +215,8 @@ __device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n
 // Out-of-line instances of the Montgomery product: the kernel body calls these (three function
 // bodies per shape: square, multiply-by-global-operand, reduce) instead of inlining seven copies,
 // which keeps the hot loop inside the instruction cache.
-template <int K, int M, int MODE>
-__device__ __noinline__ void mont_call(const WarpIO<K, M> io) {
+template <int K, int M, int MODE, bool PLN = false>
+__device__ __noinline__ void mont_call(const WarpIO<K, M, PLN> io) {
   mont_mul<K, M, MODE>(io);
 }
 

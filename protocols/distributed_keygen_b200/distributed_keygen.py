@@ -1,0 +1,121 @@
+"""
+Host-side mirror of the batch drivers of the reference's ``DistributedPaillier``
+(``distributed_keygen.py`` in tno.mpc.protocols.distributed_keygen v4.2.2) for the hot path only:
+
+* the biprimality-test v calculation (``__biprime_test_v_calculation``, ``:1056-1108``) for one
+  candidate and -- what ``compute_modulus``'s list comprehension (``:1313-1329``) becomes -- for a
+  whole batch of candidates in one grouped GPU call;
+* the biprimality verdict (``__biprime_test_with_v_i``, ``:1110-1175``);
+* the two loops of ``_decrypt_sequence_raw`` (``:463-466`` and ``:510-515``) as batched calls, for
+  the in-process (``distributed=False``) case where all parties' keys live in one process.
+
+The interactive protocol (pools, message ids, Shamir exchanges, key storage) is out of scope: see
+INTEGRATION.md for how these functions are patched into the reference.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Mapping, Sequence
+
+from .engine import modexp_grouped
+from .paillier_shared_key import PaillierSharedKey
+
+JACOBI_CORRECTION_FACTOR = 4  # distributed_keygen.py:60
+
+
+def jacobi_symbol(a: int, n: int) -> int:
+    """Jacobi symbol (a/n), n odd and positive: what ``sympy.jacobi_symbol`` returns at ``:1089``.
+    Host-side filter in front of the GPU batch (binary algorithm)."""
+    if n <= 0 or n % 2 == 0:
+        raise ValueError("n should be an odd positive integer")
+    a %= n
+    result = 1
+    while a:
+        tz = (a & -a).bit_length() - 1
+        if tz:
+            a >>= tz
+            if tz & 1 and n & 7 in (3, 5):
+                result = -result
+        a, n = n, a
+        if a & 3 == 3 and n & 3 == 3:
+            result = -result
+        a %= n
+    return result if n == 1 else 0
+
+
+def biprime_exponent(index: int, modulus: int, p_i: int, q_i: int) -> int:
+    """``:1092-1097``: party 1 uses (N - p_1 - q_1 + 1) // 4, the others (p_i + q_i) // 4."""
+    if index == 1:
+        return (modulus - p_i - q_i + 1) // 4
+    return (p_i + q_i) // 4
+
+
+def _select_g(g_values: Iterable[int], modulus: int, correct_param_biprime: int) -> list[int]:
+    """``:1084-1091``: the first ``correct_param_biprime`` g's whose Jacobi symbol is +1."""
+    picked: list[int] = []
+    for g in g_values:
+        if len(picked) == correct_param_biprime:
+            break
+        if jacobi_symbol(g, modulus) != 1:
+            continue
+        picked.append(g)
+    return picked
+
+
+def biprime_test_v_calculation_batch(
+    candidates: Sequence[tuple[Sequence[int], int, int, int]],
+    index: int,
+    correct_param_biprime: int,
+    device: int = 0,
+) -> list[list[int]]:
+    """All candidates of one ``compute_modulus`` round at once.  ``candidates`` holds
+    ``(g_values, modulus, p_i, q_i)`` per surviving candidate N (the tuple the reference's list
+    comprehension unpacks at ``:1321-1329``); returns this party's v values per candidate."""
+    moduli = [c[1] for c in candidates]
+    exps = [biprime_exponent(index, n, p_i, q_i) for (_, n, p_i, q_i) in candidates]
+    bases = [_select_g(g, n, correct_param_biprime) for (g, n, _, _) in candidates]
+    return modexp_grouped(moduli, exps, bases, device)
+
+
+def biprime_test_v_calculation(
+    g_values: Sequence[int], index: int, modulus: int, p_i: int, q_i: int, correct_param_biprime: int,
+    device: int = 0,
+) -> list[int]:
+    """Single-candidate form with the reference's argument order (``:1056-1065``); returns the list
+    the reference stores with ``batched_v_i.set_share(index, v_values)``."""
+    return biprime_test_v_calculation_batch(
+        [(g_values, modulus, p_i, q_i)], index, correct_param_biprime, device
+    )[0]
+
+
+def biprime_test_with_v_i(
+    v_by_party: Mapping[int, Sequence[int]], modulus: int, correct_param_biprime: int
+) -> bool:
+    """``:1110-1175``: N passes iff the first ``correct_param_biprime`` tests all satisfy
+    v_1 = +- prod_{i>1} v_i (mod N); running out of tests is a failure."""
+    n_tests = min(len(v) for v in v_by_party.values())
+    successful = 0
+    for k in range(n_tests):
+        product = 1
+        for key, values in v_by_party.items():
+            if key != 1:
+                product *= values[k]
+        value1 = v_by_party[1][k]
+        if not (value1 % modulus == product % modulus or value1 % modulus == -product % modulus):
+            return False
+        successful += 1
+        if successful >= correct_param_biprime:
+            return True
+    return False
+
+
+def decrypt_sequence_local(
+    keys: Mapping[int, PaillierSharedKey], ciphertexts: Sequence[object], combiner: int | None = None
+) -> list[int]:
+    """The arithmetic of ``_decrypt_sequence_raw`` (``:430-517``) when every party's key is in this
+    process: loop 1 (``:463-466``) = one batched partial decryption per party, loop 2
+    (``:510-515``) = one batched combination.  Returns the raw plaintext integers (what the
+    reference wraps in ``EncodedPlaintext``)."""
+    partials = {pid: key.partial_decrypt_batch(ciphertexts) for pid, key in keys.items()}
+    dicts = [{pid: partials[pid][i] for pid in keys} for i in range(len(ciphertexts))]
+    key = keys[combiner if combiner is not None else min(keys)]
+    return key.decrypt_batch(dicts)

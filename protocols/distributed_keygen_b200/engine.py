@@ -137,3 +137,97 @@ class CombineContext:
 
     def combine_device(self, d_partials: int, d_out: int, d_status: int, count: int, stream: int) -> None:
         _native.check(_native.lib.dkg_combine_batch_device(self._h, d_partials, d_out, d_status, count, stream))
+
+
+class EncryptContext:
+    """Batched Paillier encryption with g = N + 1 (``distributed_keygen.py:712``):
+    ``(1 + m N) * r^N mod N^2`` -- the third-party ``Paillier.encrypt`` / ``randomize`` arithmetic --
+    or just the randomness ``r^N mod N^2`` when no plaintexts are given."""
+
+    def __init__(self, n: int, device: int = 0) -> None:
+        self.n = n
+        self.n_limbs = limbs_for_bits(n.bit_length())
+        self._n = int_to_limbs(n, self.n_limbs)
+        self._ctx = ModexpContext(n * n, n, device)
+        self.n2_limbs = self._ctx.limbs
+
+    def close(self) -> None:
+        self._ctx.close()
+
+    def encrypt_limbs(self, r: np.ndarray, m: np.ndarray | None) -> np.ndarray:
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        count = r.shape[0]
+        if r.ndim != 2 or r.shape[1] != self.n_limbs:
+            raise ValueError(f"r must have shape [count, {self.n_limbs}]")
+        m_ptr = None
+        if m is not None:
+            m = np.ascontiguousarray(m, dtype=np.uint32)
+            if m.shape != r.shape:
+                raise ValueError("m must have the same shape as r")
+            m_ptr = m.ctypes.data
+        out = np.zeros((count, self.n2_limbs), dtype=np.uint32)
+        _native.check(
+            _native.lib.dkg_encrypt_batch(
+                self._ctx._h, self._n.ctypes.data, self.n_limbs, r.ctypes.data, m_ptr, out.ctypes.data, count
+            )
+        )
+        return out
+
+    def encrypt(self, plaintexts: Sequence[int], randomness: Sequence[int]) -> list[int]:
+        """Raw ciphertext values for already-encoded integer plaintexts (taken modulo N, so negative
+        values are ``N - |m|`` as in the reference's encoding)."""
+        m = ints_to_limbs([p % self.n for p in plaintexts], self.n_limbs)
+        r = ints_to_limbs([x % self.n for x in randomness], self.n_limbs)
+        return limbs_to_ints(self.encrypt_limbs(r, m))
+
+    def randomness(self, randomness: Sequence[int]) -> list[int]:
+        """``r^N mod N^2`` (what the reference's randomness pre-generation computes)."""
+        r = ints_to_limbs([x % self.n for x in randomness], self.n_limbs)
+        return limbs_to_ints(self.encrypt_limbs(r, None))
+
+
+def modexp_grouped_limbs(
+    moduli: np.ndarray, exps: np.ndarray, bases: np.ndarray, device: int = 0
+) -> np.ndarray:
+    """``out[g, k] = bases[g, k] ** exps[g] mod moduli[g]`` on limb arrays: ``moduli`` [G, L] (odd),
+    ``exps`` [G, Le], ``bases`` [G, per_group, L]."""
+    moduli = np.ascontiguousarray(moduli, dtype=np.uint32)
+    exps = np.ascontiguousarray(exps, dtype=np.uint32)
+    bases = np.ascontiguousarray(bases, dtype=np.uint32)
+    if bases.ndim != 3 or moduli.ndim != 2 or exps.ndim != 2:
+        raise ValueError("expected moduli [G, L], exps [G, Le], bases [G, per_group, L]")
+    groups, per_group, limbs = bases.shape
+    if moduli.shape != (groups, limbs) or exps.shape[0] != groups:
+        raise ValueError("shape mismatch between moduli / exps / bases")
+    out = np.zeros_like(bases)
+    _native.check(
+        _native.lib.dkg_modexp_grouped(
+            device, moduli.ctypes.data, exps.ctypes.data, exps.shape[1], bases.ctypes.data,
+            out.ctypes.data, groups, per_group, limbs,
+        )
+    )
+    return out
+
+
+def modexp_grouped(
+    moduli: Sequence[int], exps: Sequence[int], bases: Sequence[Sequence[int]], device: int = 0
+) -> list[list[int]]:
+    """Python-int wrapper: group g raises each of ``bases[g]`` to ``exps[g]`` modulo ``moduli[g]``.
+    Groups may have different numbers of bases (padded internally)."""
+    if not moduli:
+        return []
+    if any(m <= 0 or m % 2 == 0 for m in moduli):
+        raise ValueError("every modulus must be a positive odd integer")
+    if any(e < 0 for e in exps):
+        raise ValueError("grouped modexp takes non-negative exponents")
+    limbs = limbs_for_bits(max(m.bit_length() for m in moduli))
+    exp_limbs = limbs_for_bits(max(max(e.bit_length() for e in exps), 1))
+    per_group = max(max(len(b) for b in bases), 1)
+    flat: list[int] = []
+    for m, bs in zip(moduli, bases):
+        flat.extend(b % m for b in bs)
+        flat.extend([1] * (per_group - len(bs)))
+    arr = ints_to_limbs(flat, limbs).reshape(len(moduli), per_group, limbs)
+    out = modexp_grouped_limbs(ints_to_limbs(moduli, limbs), ints_to_limbs(exps, exp_limbs), arr, device)
+    vals = limbs_to_ints(out.reshape(-1, limbs))
+    return [vals[g * per_group : g * per_group + len(bs)] for g, bs in enumerate(bases)]

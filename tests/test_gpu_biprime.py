@@ -1,0 +1,62 @@
+"""GPU parity for the grouped modexp / biprimality-test batch against the values recorded from the
+reference's __biprime_test_v_calculation and __biprime_test_with_v_i (tests/golden)."""
+from __future__ import annotations
+
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _h(x: str) -> int:
+    return int(x, 16)
+
+
+def test_grouped_modexp_random():
+    import protocols.distributed_keygen_b200 as eng
+
+    rng = random.Random(41)
+    for bits, groups, per_group in [(67, 5, 3), (130, 9, 40), (515, 4, 40), (2050, 3, 40), (2048, 2, 7), (4100, 1, 33)]:
+        moduli = [rng.getrandbits(bits) | 1 | (1 << (bits - 1)) for _ in range(groups)]
+        exps = [rng.getrandbits(rng.choice([bits - 3, bits // 2, 5])) for _ in range(groups)]
+        exps[0] = 0
+        bases = [[rng.randrange(m) for _ in range(per_group if g % 2 == 0 else max(1, per_group - 2))]
+                 for g, m in enumerate(moduli)]
+        bases[0][0] = 0
+        got = eng.modexp_grouped(moduli, exps, bases)
+        want = [[pow(b, e, m) for b in bs] for m, e, bs in zip(moduli, exps, bases)]
+        assert got == want, (bits, groups)
+
+
+def test_biprime_v_values_and_verdict_match_reference(biprime_vectors):
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+
+    cases = biprime_vectors["cases"]
+    for party in (1, 2, 3):
+        batch, expect = [], []
+        for case in cases:
+            if party > case["parties"]:
+                continue
+            n = _h(case["n"])
+            g_values = [_h(g) for g in case["g_values"]]
+            batch.append((g_values, n, _h(case["p_shares"][party - 1]), _h(case["q_shares"][party - 1])))
+            expect.append([_h(v) for v in case["v"][str(party)]])
+        # one grouped call per party per key width class is what compute_modulus would issue;
+        # here all candidates of the same correctness parameter go together
+        for correct in sorted({c["correct_param_biprime"] for c in cases}):
+            idx = [i for i, c in enumerate([c for c in cases if party <= c["parties"]]) if c["correct_param_biprime"] == correct]
+            got = dkg.biprime_test_v_calculation_batch([batch[i] for i in idx], party, correct)
+            assert got == [expect[i] for i in idx], (party, correct)
+    # verdicts from the v values of all parties
+    for case in cases:
+        n = _h(case["n"])
+        v_by_party = {int(p): [_h(v) for v in vs] for p, vs in case["v"].items()}
+        if all(len(v) >= case["correct_param_biprime"] for v in v_by_party.values()):
+            assert dkg.biprime_test_with_v_i(v_by_party, n, case["correct_param_biprime"]) == case["verdict"]
+    # single-candidate form, reference argument order
+    case = cases[0]
+    g_values = [_h(g) for g in case["g_values"]]
+    v = dkg.biprime_test_v_calculation(g_values, 1, _h(case["n"]), _h(case["p_shares"][0]), _h(case["q_shares"][0]),
+                                       case["correct_param_biprime"])
+    assert v == [_h(x) for x in case["v"]["1"]]
