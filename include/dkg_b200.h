@@ -117,6 +117,23 @@ int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint32_t* exps,
                        const uint32_t* bases, uint32_t* out, size_t groups, int per_group,
                        int limbs);
 
+/* ---- the filters around the biprimality test ---------------------------- */
+/* One compute_modulus round's v calculation in one call (distributed_keygen.py:1084-1097):
+ * Jacobi symbol of each of the g_per_candidate jointly drawn g's (sympy.jacobi_symbol at :1089),
+ * the first `correct` with symbol +1 are raised to exps[g] modulo moduli[g].
+ * gvals: [groups][g_per_candidate][limbs]; out_v: [groups][correct][limbs] (rows beyond
+ * out_count[g] are zero); out_count[g] = number of usable g's found (<= correct). */
+int dkg_biprime_v_batch(int device, const uint32_t* moduli, const uint32_t* exps, int exp_limbs,
+                        const uint32_t* gvals, int g_per_candidate, int correct, uint32_t* out_v,
+                        int32_t* out_count, size_t groups, int limbs);
+/* sym[g][k] = Jacobi symbol (gvals[g][k] / moduli[g]) in {-1, 0, +1}. */
+int dkg_jacobi_batch(int device, const uint32_t* moduli, const uint32_t* gvals, int per_group,
+                     int8_t* sym, size_t groups, int limbs);
+/* flags[g] = 1 if moduli[g] is divisible by one of primes[0..nprimes)
+ * (__small_prime_divisors_test, distributed_keygen.py:1197-1209). */
+int dkg_small_prime_sieve(int device, const uint32_t* moduli, const uint32_t* primes, int nprimes,
+                          uint8_t* flags, size_t groups, int limbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,7 @@ EXPORTS = [
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
     "dkg_combine_batch", "dkg_combine_batch_device",
     "dkg_encrypt_batch", "dkg_modexp_grouped",
+    "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve",
 ]
 
 
@@ -69,6 +70,10 @@ def _load() -> ctypes.CDLL:
     lib.dkg_combine_batch_device.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t, c_void]
     lib.dkg_encrypt_batch.argtypes = [c_void, c_u32p, ctypes.c_int, c_u32p, c_u32p, c_u32p, ctypes.c_size_t]
     lib.dkg_modexp_grouped.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u32p, c_u32p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    lib.dkg_biprime_v_batch.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int,
+                                        c_u32p, c_void, ctypes.c_size_t, ctypes.c_int]
+    lib.dkg_jacobi_batch.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_void, ctypes.c_size_t, ctypes.c_int]
+    lib.dkg_small_prime_sieve.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u8p, ctypes.c_size_t, ctypes.c_int]
     return lib
 
 

@@ -16,6 +16,7 @@
 #include "dkg_combine.cuh"
 #include "dkg_aux_kernels.cuh"
 #include "dkg_grouped_params_fwd.h"
+#include "dkg_biprime.cuh"
 
 namespace {
 
@@ -579,6 +580,71 @@ dkg::GroupedFn lookup_grouped(int K, int M) {
 }
 }  // namespace
 
+namespace {
+
+struct GroupedPlan {
+  Shape shape{};
+  dkg::GroupedFn kernel = nullptr;
+  int Lp = 0, K = 0, wbits = 1, ndigits = 1, warps = 1, ctas = 1;
+  size_t smem = 0, q_off = 0, scratch_per_warp = 0;
+};
+
+int plan_grouped(DeviceState* d, int limbs, int ebits, size_t count, GroupedPlan* plan) {
+  for (const Shape& sh : kShapes)
+    if (sh.K * sh.M >= limbs && (plan->kernel = lookup_grouped(sh.K, sh.M)) != nullptr) { plan->shape = sh; break; }
+  if (!plan->kernel) return fail(DKG_ERR_UNSUPPORTED, "modulus wider than the grouped kernel shapes (132 limbs)");
+  plan->Lp = plan->shape.K * plan->shape.M;
+  plan->K = plan->shape.K;
+  plan->wbits = choose_window(ebits);
+  plan->ndigits = std::max(1, (ebits + plan->wbits - 1) / plan->wbits);
+  const size_t per_warp_smem = ((size_t)2 * plan->Lp + plan->K) * 32 * 4;
+  plan->warps = (int)std::min<size_t>(DKG_MAX_THREADS / 32, kMaxDynSmem / per_warp_smem);
+  if (plan->warps < 1) return fail(DKG_ERR_UNSUPPORTED, "operand too wide for shared memory");
+  plan->smem = per_warp_smem * plan->warps;
+  const size_t tsize = ((size_t)1 << plan->wbits) - 1;
+  plan->q_off = std::max<size_t>(tsize, 1) * (size_t)plan->Lp * 32;
+  plan->scratch_per_warp = plan->q_off + (size_t)3 * plan->Lp * 32;  // Q | R2 | ONER in lane layout
+  const unsigned long long nwork = (count + 31) / 32;
+  plan->ctas = d->sm_count;
+  if (nwork < (unsigned long long)plan->ctas * plan->warps) plan->ctas = (int)((nwork + plan->warps - 1) / plan->warps);
+  int rc = ensure_scratch(d, (size_t)d->sm_count * plan->warps * plan->scratch_per_warp);
+  if (rc != DKG_OK) return rc;
+  cudaError_t e = cudaFuncSetAttribute((const void*)plan->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem);
+  if (e != cudaSuccess) return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute(grouped): ") + cudaGetErrorString(e));
+  return DKG_OK;
+}
+
+// enqueue setup + grouped modexp on device buffers (gconsts/digits are caller-allocated scratch)
+int launch_grouped(DeviceState* d, const GroupedPlan& plan, const uint32_t* d_mod, const uint32_t* d_exp, int exp_limbs,
+                   const uint32_t* d_bases, uint32_t* d_out, size_t groups, int per_group, int limbs,
+                   uint32_t* d_gc, uint8_t* d_dig) {
+  CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), d->stream));
+  dkg::GroupedParams p{};
+  p.moduli = d_mod; p.exps = d_exp; p.bases = d_bases; p.out = d_out; p.groups = groups;
+  p.per_group = per_group; p.limbs = limbs; p.exp_limbs = exp_limbs; p.K = plan.K; p.Lp = plan.Lp;
+  p.wbits = plan.wbits; p.ndigits = plan.ndigits; p.gconsts = d_gc; p.digits = d_dig; p.scratch = d->scratch;
+  p.scratch_per_warp = plan.scratch_per_warp; p.scratch_q_offset = plan.q_off; p.counter = d->counter;
+  dkg::launch_group_setup(p, d->stream);
+  plan.kernel<<<plan.ctas, plan.warps * 32, plan.smem, d->stream>>>(p);
+  g_launches.fetch_add(2);
+  CUDA_TRY(cudaGetLastError());
+  return DKG_OK;
+}
+
+struct DevBufs {
+  std::vector<void*> ptrs;
+  ~DevBufs() { for (void* p : ptrs) if (p) cudaFree(p); }
+  template <typename T> cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T*)p;
+    return e;
+  }
+};
+
+}  // namespace
+
 extern "C" int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint32_t* exps, int exp_limbs,
                                   const uint32_t* bases, uint32_t* out, size_t groups, int per_group, int limbs) {
   if (!moduli || !exps || !bases || !out || exp_limbs <= 0 || per_group <= 0 || limbs <= 0)
@@ -586,71 +652,156 @@ extern "C" int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint
   if (groups == 0) return DKG_OK;
   for (size_t g = 0; g < groups; ++g)
     if ((moduli[g * (size_t)limbs] & 1u) == 0) return fail(DKG_ERR_INVALID, "every modulus must be odd");
-  Shape shape;
-  dkg::GroupedFn kernel = nullptr;
-  for (const Shape& sh : kShapes)
-    if (sh.K * sh.M >= limbs && (kernel = lookup_grouped(sh.K, sh.M)) != nullptr) { shape = sh; break; }
-  if (!kernel) return fail(DKG_ERR_UNSUPPORTED, "modulus wider than the grouped kernel shapes (132 limbs)");
   DeviceState* d = nullptr;
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  const int Lp = shape.K * shape.M, K = shape.K;
   int ebits = 0;
   for (size_t g = 0; g < groups; ++g) ebits = std::max(ebits, dkg_host::bit_length(exps + g * (size_t)exp_limbs, exp_limbs));
-  const int wbits = choose_window(ebits);
-  const int ndigits = std::max(1, (ebits + wbits - 1) / wbits);
-
   const size_t count = groups * (size_t)per_group;
-  const size_t vw = (K % 4 == 0) ? 4 : 2;
-  const size_t per_warp_smem = ((size_t)2 * Lp + K) * 32 * 4;
-  (void)vw;
-  int warps = (int)std::min<size_t>(DKG_MAX_THREADS / 32, kMaxDynSmem / per_warp_smem);
-  if (warps < 1) return fail(DKG_ERR_UNSUPPORTED, "operand too wide for shared memory");
-  const size_t smem = per_warp_smem * warps;
-  const size_t tsize = ((size_t)1 << wbits) - 1;
-  const size_t q_off = std::max<size_t>(tsize, 1) * (size_t)Lp * 32;
-  const size_t scratch_per_warp = q_off + (size_t)3 * Lp * 32;  // Q | R2 | ONER in lane layout
-  const unsigned long long nwork = (count + 31) / 32;
-  int ctas = d->sm_count;
-  if (nwork < (unsigned long long)ctas * warps) ctas = (int)((nwork + warps - 1) / warps);
-  rc = ensure_scratch(d, (size_t)d->sm_count * warps * scratch_per_warp);
+  GroupedPlan plan;
+  rc = plan_grouped(d, limbs, ebits, count, &plan);
   if (rc != DKG_OK) return rc;
-  cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute(grouped): ") + cudaGetErrorString(e));
-
-  uint32_t *d_mod = nullptr, *d_exp = nullptr, *d_bases = nullptr, *d_out = nullptr, *d_gc = nullptr;
-  uint8_t* d_dig = nullptr;
+  DevBufs bufs;
+  uint32_t *d_mod, *d_exp, *d_bases, *d_out, *d_gc;
+  uint8_t* d_dig;
   const size_t mod_b = groups * (size_t)limbs * 4, exp_b = groups * (size_t)exp_limbs * 4, base_b = count * (size_t)limbs * 4;
-  e = cudaMalloc(&d_mod, mod_b);
-  if (e == cudaSuccess) e = cudaMalloc(&d_exp, exp_b);
-  if (e == cudaSuccess) e = cudaMalloc(&d_bases, base_b);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, base_b);
-  if (e == cudaSuccess) e = cudaMalloc(&d_gc, groups * (size_t)(3 * Lp + K) * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&d_dig, groups * (size_t)ndigits);
-  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("grouped cudaMalloc: ") + cudaGetErrorString(e));
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_exp, exps, exp_b, cudaMemcpyHostToDevice, d->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases, bases, base_b, cudaMemcpyHostToDevice, d->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
+  cudaError_t e = bufs.alloc(&d_mod, mod_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_exp, exp_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_bases, base_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_out, base_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_gc, groups * (size_t)(3 * plan.Lp + plan.K) * 4);
+  if (e == cudaSuccess) e = bufs.alloc(&d_dig, groups * (size_t)plan.ndigits);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("grouped cudaMalloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_exp, exps, exp_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_bases, bases, base_b, cudaMemcpyHostToDevice, d->stream));
+  rc = launch_grouped(d, plan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, per_group, limbs, d_gc, d_dig);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, base_b, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
+}
+
+// Whole v calculation of one compute_modulus round: Jacobi filter, selection of the first
+// `correct` usable g's per candidate, grouped modexp.
+extern "C" int dkg_biprime_v_batch(int device, const uint32_t* moduli, const uint32_t* exps, int exp_limbs,
+                                   const uint32_t* gvals, int g_per_candidate, int correct, uint32_t* out_v,
+                                   int32_t* out_count, size_t groups, int limbs) {
+  if (!moduli || !exps || !gvals || !out_v || !out_count || exp_limbs <= 0 || g_per_candidate <= 0 || correct <= 0 || limbs <= 0)
+    return fail(DKG_ERR_INVALID, "null/empty argument");
+  if (limbs > dkg::kGroupedMaxLimbs) return fail(DKG_ERR_UNSUPPORTED, "candidate wider than the biprime kernels support");
+  if (groups == 0) return DKG_OK;
+  for (size_t g = 0; g < groups; ++g)
+    if ((moduli[g * (size_t)limbs] & 1u) == 0) return fail(DKG_ERR_INVALID, "every modulus must be odd");
+  DeviceState* d = nullptr;
+  int rc = device_state(device, &d);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  int ebits = 0;
+  for (size_t g = 0; g < groups; ++g) ebits = std::max(ebits, dkg_host::bit_length(exps + g * (size_t)exp_limbs, exp_limbs));
+  const size_t count = groups * (size_t)correct;
+  GroupedPlan plan;
+  rc = plan_grouped(d, limbs, ebits, count, &plan);
+  if (rc != DKG_OK) return rc;
+  DevBufs bufs;
+  uint32_t *d_mod, *d_exp, *d_g, *d_bases, *d_out, *d_gc;
+  uint8_t* d_dig;
+  int8_t* d_sym;
+  int *d_pick, *d_count;
+  const size_t mod_b = groups * (size_t)limbs * 4, exp_b = groups * (size_t)exp_limbs * 4;
+  const size_t g_b = groups * (size_t)g_per_candidate * limbs * 4, base_b = count * (size_t)limbs * 4;
+  cudaError_t e = bufs.alloc(&d_mod, mod_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_exp, exp_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_g, g_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_bases, base_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_out, base_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_gc, groups * (size_t)(3 * plan.Lp + plan.K) * 4);
+  if (e == cudaSuccess) e = bufs.alloc(&d_dig, groups * (size_t)plan.ndigits);
+  if (e == cudaSuccess) e = bufs.alloc(&d_sym, groups * (size_t)g_per_candidate);
+  if (e == cudaSuccess) e = bufs.alloc(&d_pick, count * sizeof(int));
+  if (e == cudaSuccess) e = bufs.alloc(&d_count, groups * sizeof(int));
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("biprime cudaMalloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_exp, exps, exp_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_g, gvals, g_b, cudaMemcpyHostToDevice, d->stream));
+  const unsigned long long nsym = groups * (unsigned long long)g_per_candidate;
+  dkg::jacobi_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, d->stream>>>(d_mod, d_g, limbs, groups, g_per_candidate, d_sym);
+  dkg::select_g_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, d->stream>>>(d_sym, groups, g_per_candidate, correct, d_pick, d_count);
+  const unsigned gblocks = (unsigned)std::min<size_t>((count * limbs + 255) / 256, 148 * 32);
+  dkg::gather_g_kernel<<<gblocks, 256, 0, d->stream>>>(d_g, d_pick, limbs, groups, g_per_candidate, correct, d_bases);
+  g_launches.fetch_add(3);
+  CUDA_TRY(cudaGetLastError());
+  rc = launch_grouped(d, plan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, correct, limbs, d_gc, d_dig);
+  if (rc != DKG_OK) return rc;
+  dkg::clear_unused_kernel<<<gblocks, 256, 0, d->stream>>>(d_out, d_count, limbs, groups, correct);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out_v, d_out, base_b, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(out_count, d_count, groups * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
+}
+
+// Jacobi symbols only: sym[g][k] = (gvals[g][k] / moduli[g]) in {-1, 0, 1}
+extern "C" int dkg_jacobi_batch(int device, const uint32_t* moduli, const uint32_t* gvals, int per_group, int8_t* sym,
+                                size_t groups, int limbs) {
+  if (!moduli || !gvals || !sym || per_group <= 0 || limbs <= 0) return fail(DKG_ERR_INVALID, "null/empty argument");
+  if (limbs > dkg::kGroupedMaxLimbs) return fail(DKG_ERR_UNSUPPORTED, "operand wider than the Jacobi kernel supports");
+  if (groups == 0) return DKG_OK;
+  for (size_t g = 0; g < groups; ++g)
+    if ((moduli[g * (size_t)limbs] & 1u) == 0) return fail(DKG_ERR_INVALID, "every modulus must be odd");
+  DeviceState* d = nullptr;
+  int rc = device_state(device, &d);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  DevBufs bufs;
+  uint32_t *d_mod, *d_g;
+  int8_t* d_sym;
+  const size_t mod_b = groups * (size_t)limbs * 4, g_b = groups * (size_t)per_group * limbs * 4;
+  cudaError_t e = bufs.alloc(&d_mod, mod_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_g, g_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_sym, groups * (size_t)per_group);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("jacobi cudaMalloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_g, gvals, g_b, cudaMemcpyHostToDevice, d->stream));
+  const unsigned long long nsym = groups * (unsigned long long)per_group;
+  dkg::jacobi_kernel<<<(unsigned)((nsym + 127) / 128), 128, 0, d->stream>>>(d_mod, d_g, limbs, groups, per_group, d_sym);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(sym, d_sym, groups * (size_t)per_group, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
+}
+
+// flags[g] = 1 if moduli[g] has a divisor among primes[0..nprimes)
+extern "C" int dkg_small_prime_sieve(int device, const uint32_t* moduli, const uint32_t* primes, int nprimes,
+                                     uint8_t* flags, size_t groups, int limbs) {
+  if (!moduli || !primes || !flags || nprimes <= 0 || limbs <= 0) return fail(DKG_ERR_INVALID, "null/empty argument");
+  if (groups == 0) return DKG_OK;
+  for (int k = 0; k < nprimes; ++k)
+    if (primes[k] < 2) return fail(DKG_ERR_INVALID, "primes must be >= 2");
+  DeviceState* d = nullptr;
+  int rc = device_state(device, &d);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  DevBufs bufs;
+  uint32_t *d_mod, *d_pr;
+  uint8_t* d_fl;
+  const size_t mod_b = groups * (size_t)limbs * 4;
+  cudaError_t e = bufs.alloc(&d_mod, mod_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_pr, (size_t)nprimes * 4);
+  if (e == cudaSuccess) e = bufs.alloc(&d_fl, groups);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("sieve cudaMalloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_pr, primes, (size_t)nprimes * 4, cudaMemcpyHostToDevice, d->stream));
+  for (size_t off = 0; off < groups; off += 65535u * 32u) {
+    const size_t n = std::min<size_t>(groups - off, 65535u * 32u);
+    dkg::small_prime_sieve_kernel<<<(unsigned)n, 128, 0, d->stream>>>(d_mod + off * limbs, limbs, n, d_pr, nprimes, d_fl + off);
+    g_launches.fetch_add(1);
   }
-  if (rc == DKG_OK) {
-    dkg::GroupedParams p{};
-    p.moduli = d_mod; p.exps = d_exp; p.bases = d_bases; p.out = d_out; p.groups = groups;
-    p.per_group = per_group; p.limbs = limbs; p.exp_limbs = exp_limbs; p.K = K; p.Lp = Lp;
-    p.wbits = wbits; p.ndigits = ndigits; p.gconsts = d_gc; p.digits = d_dig; p.scratch = d->scratch;
-    p.scratch_per_warp = scratch_per_warp; p.scratch_q_offset = q_off; p.counter = d->counter;
-    dkg::launch_group_setup(p, d->stream);
-    kernel<<<ctas, warps * 32, smem, d->stream>>>(p);
-    g_launches.fetch_add(2);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, base_b, cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("grouped modexp: ") + cudaGetErrorString(e));
-  }
-  for (void* ptr : {(void*)d_mod, (void*)d_exp, (void*)d_bases, (void*)d_out, (void*)d_gc, (void*)d_dig})
-    if (ptr) cudaFree(ptr);
-  return rc;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(flags, d_fl, groups, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
 }

@@ -16,7 +16,10 @@ from __future__ import annotations
 
 from typing import Iterable, Mapping, Sequence
 
-from .engine import modexp_grouped
+import numpy as np
+
+from .engine import biprime_v_batch_limbs, modexp_grouped, small_prime_sieve
+from .limbs import ints_to_limbs, limbs_for_bits, limbs_to_ints
 from .paillier_shared_key import PaillierSharedKey
 
 JACOBI_CORRECTION_FACTOR = 4  # distributed_keygen.py:60
@@ -70,8 +73,25 @@ def biprime_test_v_calculation_batch(
     """All candidates of one ``compute_modulus`` round at once.  ``candidates`` holds
     ``(g_values, modulus, p_i, q_i)`` per surviving candidate N (the tuple the reference's list
     comprehension unpacks at ``:1321-1329``); returns this party's v values per candidate."""
+    if not candidates:
+        return []
     moduli = [c[1] for c in candidates]
     exps = [biprime_exponent(index, n, p_i, q_i) for (_, n, p_i, q_i) in candidates]
+    ng = len(candidates[0][0])
+    if ng > 0 and all(len(c[0]) == ng for c in candidates) and min(exps) >= 0:
+        # everything on the device: Jacobi filter, selection, grouped modexp (one call)
+        limbs = limbs_for_bits(max(n.bit_length() for n in moduli))
+        exp_limbs = limbs_for_bits(max(max(e.bit_length() for e in exps), 1))
+        flat = [g % n for (gs, n, _, _) in candidates for g in gs]
+        g_arr = ints_to_limbs(flat, limbs).reshape(len(candidates), ng, limbs)
+        v, count = biprime_v_batch_limbs(
+            ints_to_limbs(moduli, limbs), ints_to_limbs(exps, exp_limbs), g_arr,
+            min(correct_param_biprime, ng), device,
+        )
+        c_eff = v.shape[1]
+        vals = limbs_to_ints(v.reshape(-1, limbs))
+        return [vals[i * c_eff : i * c_eff + int(count[i])] for i in range(len(candidates))]
+    # ragged g lists: filter on the host, then one grouped modexp
     bases = [_select_g(g, n, correct_param_biprime) for (g, n, _, _) in candidates]
     return modexp_grouped(moduli, exps, bases, device)
 
@@ -106,6 +126,12 @@ def biprime_test_with_v_i(
         if successful >= correct_param_biprime:
             return True
     return False
+
+
+def small_prime_divisors_test_batch(prime_list: Sequence[int], moduli: Sequence[int], device: int = 0) -> list[bool]:
+    """``__small_prime_divisors_test`` (``:1197-1209``) for all candidates of a round at once (the
+    filter of ``:1288-1292``): ``True`` where N has a divisor in ``prime_list``."""
+    return small_prime_sieve(moduli, prime_list, device)
 
 
 def decrypt_sequence_local(

@@ -231,3 +231,65 @@ def modexp_grouped(
     out = modexp_grouped_limbs(ints_to_limbs(moduli, limbs), ints_to_limbs(exps, exp_limbs), arr, device)
     vals = limbs_to_ints(out.reshape(-1, limbs))
     return [vals[g * per_group : g * per_group + len(bs)] for g, bs in enumerate(bases)]
+
+
+def biprime_v_batch_limbs(
+    moduli: np.ndarray, exps: np.ndarray, gvals: np.ndarray, correct: int, device: int = 0
+) -> tuple[np.ndarray, np.ndarray]:
+    """Fused v calculation of one ``compute_modulus`` round on limb arrays: Jacobi filter, the
+    first ``correct`` usable g's per candidate, grouped modexp.  ``moduli`` [G, L], ``exps`` [G, Le],
+    ``gvals`` [G, NG, L].  Returns (v [G, correct, L], count [G])."""
+    moduli = np.ascontiguousarray(moduli, dtype=np.uint32)
+    exps = np.ascontiguousarray(exps, dtype=np.uint32)
+    gvals = np.ascontiguousarray(gvals, dtype=np.uint32)
+    groups, ng, limbs = gvals.shape
+    if moduli.shape != (groups, limbs) or exps.shape[0] != groups:
+        raise ValueError("shape mismatch between moduli / exps / gvals")
+    out = np.zeros((groups, correct, limbs), dtype=np.uint32)
+    count = np.zeros(groups, dtype=np.int32)
+    _native.check(
+        _native.lib.dkg_biprime_v_batch(
+            device, moduli.ctypes.data, exps.ctypes.data, exps.shape[1], gvals.ctypes.data, ng, correct,
+            out.ctypes.data, count.ctypes.data, groups, limbs,
+        )
+    )
+    return out, count
+
+
+def jacobi_batch(moduli: Sequence[int], gvals: Sequence[Sequence[int]], device: int = 0) -> list[list[int]]:
+    """Jacobi symbols (g / N) for every g of every candidate N (odd), on the GPU."""
+    if not moduli:
+        return []
+    if any(m <= 0 or m % 2 == 0 for m in moduli):
+        raise ValueError("n should be an odd positive integer")
+    limbs = limbs_for_bits(max(m.bit_length() for m in moduli))
+    per_group = max(max(len(g) for g in gvals), 1)
+    flat: list[int] = []
+    for m, gs in zip(moduli, gvals):
+        flat.extend(g % m for g in gs)
+        flat.extend([0] * (per_group - len(gs)))
+    g_arr = ints_to_limbs(flat, limbs)
+    m_arr = ints_to_limbs(moduli, limbs)
+    sym = np.zeros((len(moduli), per_group), dtype=np.int8)
+    _native.check(
+        _native.lib.dkg_jacobi_batch(device, m_arr.ctypes.data, g_arr.ctypes.data, per_group, sym.ctypes.data,
+                                     len(moduli), limbs)
+    )
+    return [[int(x) for x in sym[i, : len(gs)]] for i, gs in enumerate(gvals)]
+
+
+def small_prime_sieve(moduli: Sequence[int], primes: Sequence[int], device: int = 0) -> list[bool]:
+    """``True`` where the candidate has a divisor in ``primes`` (all < 2^32)."""
+    if not moduli:
+        return []
+    if not primes:
+        return [False] * len(moduli)
+    limbs = limbs_for_bits(max(max(m.bit_length() for m in moduli), 1))
+    m_arr = ints_to_limbs(moduli, limbs)
+    p_arr = np.ascontiguousarray(np.array(list(primes), dtype=np.uint64).astype(np.uint32))
+    flags = np.zeros(len(moduli), dtype=np.uint8)
+    _native.check(
+        _native.lib.dkg_small_prime_sieve(device, m_arr.ctypes.data, p_arr.ctypes.data, len(p_arr), flags.ctypes.data,
+                                          len(moduli), limbs)
+    )
+    return [bool(x) for x in flags]

@@ -60,3 +60,59 @@ def test_biprime_v_values_and_verdict_match_reference(biprime_vectors):
     v = dkg.biprime_test_v_calculation(g_values, 1, _h(case["n"]), _h(case["p_shares"][0]), _h(case["q_shares"][0]),
                                        case["correct_param_biprime"])
     assert v == [_h(x) for x in case["v"]["1"]]
+
+
+def test_jacobi_and_sieve_on_gpu(biprime_vectors):
+    import sympy
+
+    import protocols.distributed_keygen_b200 as eng
+    from oracle import paillier_oracle as po
+
+    rng = random.Random(8)
+    moduli, gvals = [], []
+    for bits in [8, 33, 67, 130, 515, 2050, 4100]:
+        for _ in range(3):
+            n = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+            moduli.append(n)
+            gvals.append([0, 1, n - 1, 2] + [rng.randrange(n) for _ in range(20)])
+    moduli.append(3 * 5 * 7 * 11)
+    gvals.append(list(range(0, 24)))
+    got = eng.jacobi_batch(moduli, gvals)
+    for n, gs, row in zip(moduli, gvals, got):
+        assert row == [po.jacobi(g, n) for g in gs], n.bit_length()
+    # the recorded reference candidates: symbols drive the same selection as the reference made
+    case = biprime_vectors["cases"][3]
+    n = _h(case["n"])
+    gs = [_h(g) for g in case["g_values"]]
+    sym = eng.jacobi_batch([n], [gs])[0]
+    assert sym == [int(sympy.jacobi_symbol(g, n)) for g in gs]
+    # sieve (distributed_keygen.py:1197-1209) with the reference's default prime list bound 2000
+    primes = list(sympy.primerange(3, 2000))
+    cands = [rng.getrandbits(2050) | 1 for _ in range(300)] + [1000003 * 999983, 1999 * (rng.getrandbits(2000) | 1), 3]
+    assert eng.small_prime_sieve(cands, primes) == [po.small_prime_divisors_test(primes, c) for c in cands]
+
+
+def test_biprime_round_fused_many_candidates():
+    """A compute_modulus-sized round: 60 candidates x 160 g's, party 1 and party 2, against the
+    oracle (Jacobi filter + selection + modexp all on the device)."""
+    from oracle import keys as okeys
+    from oracle import paillier_oracle as po
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+
+    rng = random.Random(21)
+    pl, correct = 256, 40
+    cands = []
+    for _ in range(60):
+        p_sh = [okeys.prime_candidate_share(i + 1, pl, rng) for i in range(3)]
+        q_sh = [okeys.prime_candidate_share(i + 1, pl, rng) for i in range(3)]
+        n = sum(p_sh) * sum(q_sh)
+        gs = [rng.randint(0, n) % n for _ in range(correct * dkg.JACOBI_CORRECTION_FACTOR)]
+        cands.append((gs, n, p_sh, q_sh))
+    # one candidate with almost no usable g (all g = 0 -> symbol 0)
+    gs0, n0, p0, q0 = cands[7]
+    cands[7] = ([0] * 155 + gs0[:5], n0, p0, q0)
+    for party in (1, 2):
+        batch = [(gs, n, p_sh[party - 1], q_sh[party - 1]) for (gs, n, p_sh, q_sh) in cands]
+        got = dkg.biprime_test_v_calculation_batch(batch, party, correct)
+        want = [po.biprime_v_calculation(gs, party, n, p_i, q_i, correct) for (gs, n, p_i, q_i) in batch]
+        assert got == want

@@ -121,3 +121,24 @@ def test_shard_bounds():
     assert all(lo % 40 == 0 and hi % 40 == 0 for lo, hi in shards) and shards[-1][1] == 520
     with pytest.raises(ValueError):
         shard_bounds(10, 2, 2)
+
+
+def test_key_blob_reader_on_reference_fixtures(fixture_vectors):
+    """The 24 stored keys of the reference's test suite through the product's own reader."""
+    from oracle import keys as okeys
+    from protocols.distributed_keygen_b200.keyio import load_private_key_from_bytes
+
+    seen = 0
+    for entry in fixture_vectors["sets"]:
+        for k in entry["keys"]:
+            blob = base64.b64decode(k["blob_b64"])
+            stored = load_private_key_from_bytes(blob)
+            want = okeys.key_from_blob(blob)
+            key = stored.secret_key
+            assert (key.n, key.t, key.player_id, key.theta) == (want.n, want.t, want.player_id, want.theta)
+            assert key.share.shares == want.share.shares and key.share.degree == want.share.degree
+            assert stored.g == stored.n + 1 and stored.corruption_threshold == entry["t"]
+            assert stored.index == key.player_id and stored.precision == 8
+            assert key.partial_decrypt_exponent() == want.partial_decrypt_exponent()
+            seen += 1
+    assert seen == 24
