@@ -55,6 +55,16 @@ __device__ __forceinline__ void ldg_vec(uint2& v, const uint2* p) {
   asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
 }
 
+// predicated generic loads (the register keeps its value when the predicate is off)
+__device__ __forceinline__ void ld_generic_pred(uint32_t* r, const char* p, uint32_t on, uint4) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"(on) : "memory");
+}
+__device__ __forceinline__ void ld_generic_pred(uint32_t* r, const char* p, uint32_t on, uint2) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.v2.u32 {%0, %1}, [%2];\n\t}"
+               : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"(on) : "memory");
+}
+
 // IO policy of dkg::mont_mul for one thread of a warp.
 //  xs      shared-space byte address of this lane's vector 0 of X (consecutive vectors of one
 //          lane are 32 vectors apart); ns/nis: the CTA-uniform modulus and block inverse;
@@ -87,14 +97,22 @@ struct WarpIO {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Qg + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
   }
-  __device__ __forceinline__ void prefetch_x(int i, int v, uint32_t (&r)[K]) const {
-    V t; lds_vec(t, xs + (uint32_t)(i * KV + v) * 32u * VB); unpack(t, &r[v * VW]);
+  // Prefetch descriptor: generic address of vector 0 of the block, byte stride between vectors,
+  // and an on/off flag.  X blocks are addressed through the generic window of shared memory so
+  // that one predicated generic load serves all three sources.
+  struct Prefetch { const char* base; uint32_t stride; uint32_t on; };
+  __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
+    Prefetch d;
+    d.on = (kind == PAIR_XY || kind == PAIR_XX || kind == PAIR_NQ) ? 1u : 0u;
+    const char* xg = reinterpret_cast<const char*>(__cvta_shared_to_generic((size_t)xs)) + (size_t)(blk * KV) * 32u * VB;
+    const char* yg = reinterpret_cast<const char*>(Y + (size_t)(blk * KV) * ystride);
+    const char* qg = reinterpret_cast<const char*>(Qg + (size_t)(blk * KV) * 32);
+    d.base = kind == PAIR_XY ? yg : (kind == PAIR_XX ? xg : qg);
+    d.stride = kind == PAIR_XY ? (uint32_t)ystride * VB : 32u * VB;
+    return d;
   }
-  __device__ __forceinline__ void prefetch_y(int j, int v, uint32_t (&r)[K]) const {
-    V t; ldg_vec(t, Y + (size_t)(j * KV + v) * ystride); unpack(t, &r[v * VW]);
-  }
-  __device__ __forceinline__ void prefetch_q(int i, int v, uint32_t (&r)[K]) const {
-    V t; ldg_vec(t, Qg + (size_t)(i * KV + v) * 32); unpack(t, &r[v * VW]);
+  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
+    ld_generic_pred(&r[v * VW], d.base + (size_t)v * d.stride, d.on, V());
   }
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
 #pragma unroll

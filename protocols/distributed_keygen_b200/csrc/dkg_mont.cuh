@@ -61,11 +61,13 @@ struct PairDesc {
 };
 
 // acc += x * y.  y[j] is dead once row j is done, so while this product runs, y is refilled behind
-// the scan with the y operand of the NEXT block product (kind nk, block ny): vector v is fetched
-// right after the rows that used vector v.  Register-level double buffering: the L2/global latency
-// of Q blocks and table entries hides under the ~1000 multiplier cycles of this product.
+// the scan with the y operand of the NEXT block product (descriptor pf from io.prefetch_desc):
+// vector v is fetched right after the rows that used vector v.  Register-level double buffering:
+// the L2/global latency of Q blocks and table entries hides under the ~1000 multiplier cycles of
+// this product.
 template <int K, class IO>
-DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], const IO& io, int nk, int ny) {
+DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], const IO& io,
+                      const typename IO::Prefetch& pf) {
   static_assert(K % 2 == 0 && K >= 4, "K must be even and >= 4");
   constexpr int VW = IO::VW;
 #pragma unroll
@@ -89,12 +91,8 @@ DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], co
       for (int i = 2; i < K; i += 2) madc_cc(a.O[i + j - 1], a.O[i + j], x[i], y[j]);
       addc(a.CO[(j - 1) / 2], 0);  // O limb j+K-1
     }
-    if ((j + 1) % VW == 0) {
-      const int v = (j + 1) / VW - 1;
-      if (nk == PAIR_XY) io.prefetch_y(ny, v, y);
-      else if (nk == PAIR_XX) io.prefetch_x(ny, v, y);
-      else if (nk == PAIR_NQ) io.prefetch_q(ny, v, y);
-    }
+    // one predicated load, no branch: the block product stays a single basic block
+    if ((j + 1) % VW == 0) io.prefetch_load(pf, (j + 1) / VW - 1, y);
   }
 }
 
@@ -192,7 +190,7 @@ struct ColPlan {
 
 // IO policy (all indices are block indices; r has K limbs; VW = limbs per vector):
 //   load_x(i, r)  load_y(j, r)  load_q(i, r)  load_n(j, r)  load_ninv(r)
-//   prefetch_x(i, v, r)  prefetch_y(j, v, r)  prefetch_q(i, v, r)   (vector v of the block)
+//   prefetch_desc(kind, block) -> IO::Prefetch ; prefetch_load(desc, v, r)   (vector v of the block)
 //   store_q(i, r) store_x(i, r)
 //
 // MONT_MUL : X <- X * Y * R^-1 mod N
@@ -274,7 +272,7 @@ DKG_HD void mont_mul(const IO& io) {
         const ColPlan<M, MODE> np(c + 1);
         if (np.total > 0) nx = np.at(c + 1, 0);
       }
-      block_mac<K>(a, xb, yb, io, nx.kind, nx.yi);
+      block_mac<K>(a, xb, yb, io, io.prefetch_desc(nx.kind, nx.yi));
       if (nx.kind == PAIR_XY || nx.kind == PAIR_XX) io.load_x(nx.xi, xb);
       else if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
     }

@@ -1,10 +1,12 @@
 // Integer-multiplier roofline probe: register-resident multiply-accumulate loops with no memory
 // traffic, timed with CUDA events.  Two flavours, because they issue at different rates on sm_100a
 // (measured, profiles/r01_imad_microbench_*.txt):
-//   plain : mad.wide.u32 d, a, b, d            -> IMAD.WIDE.U32        (64-bit accumulate, no carry)
+//   plain : mad.wide.u32 d, a, b, d            -> IMAD.WIDE.U32 (64-bit accumulate, no carry), or
+//                                                 IMAD.WIDE.U32(RZ) + IADD3/IADD3.X where ptxas splits it
 //   carry : mad.lo.cc / madc.hi.cc chains      -> IMAD.WIDE.U32.X      (carry in/out via predicate)
-// The engine's schoolbook products need the carry form; the plain form is the unconditional
-// ceiling of the multiplier and is what roofline.peak reports.
+// ptxas schedules every IMAD.WIDE at a 4-cycle issue interval per SM sub-partition (32 lanes / 4
+// cycles x 4 sub-partitions = 32 wide-MAC/clk/SM, 9.3 T/s at 1965 MHz); both probes measure how
+// close register-resident code gets to that.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,19 +17,29 @@
 namespace {
 
 __global__ void peak_plain_kernel(uint32_t* out, int iters, uint32_t seed) {
-  uint64_t acc[8];
-  uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 12345u + seed;
+  // 64 distinct products a[i]*b[j] per iteration into 16 accumulators; the operands change every
+  // iteration so that nothing is loop-invariant (an earlier version with constant operands was
+  // folded by ptxas into a handful of instructions and reported a fictitious 2x rate).
+  uint64_t acc[16];
+  uint32_t a[8], b[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = (uint64_t)(a + i) << 17;
+  for (int i = 0; i < 8; i++) {
+    a[i] = threadIdx.x * 2654435761u + seed + i * 97u;
+    b[i] = blockIdx.x * 40503u + 12345u + seed * (i + 3);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = (uint64_t)(a[i & 7] + i) << 17;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+      for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[(i + j) & 15]) : "r"(a[i]), "r"(b[j]));
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] ^= (uint32_t)it; b[i] += (uint32_t)it; }
   }
   uint64_t r = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) r ^= acc[i];
+  for (int i = 0; i < 16; i++) r ^= acc[i];
   if (r == 0x123456789ull) out[0] = (uint32_t)r;
 }
 

@@ -15,9 +15,16 @@ struct HostIO {
   void load_n(int j, uint32_t (&r)[K]) const { std::memcpy(r, N + j * K, K * 4); }
   void load_ninv(uint32_t (&r)[K]) const { std::memcpy(r, NI, K * 4); }
   static constexpr int VW = (K % 4 == 0) ? 4 : 2;
-  void prefetch_y(int j, int v, uint32_t (&r)[K]) const { std::memcpy(r + v * VW, Y + j * K + v * VW, VW * 4); }
-  void prefetch_x(int i, int v, uint32_t (&r)[K]) const { std::memcpy(r + v * VW, X + i * K + v * VW, VW * 4); }
-  void prefetch_q(int i, int v, uint32_t (&r)[K]) const { std::memcpy(r + v * VW, Q + i * K + v * VW, VW * 4); }
+  struct Prefetch { const uint32_t* base; };
+  Prefetch prefetch_desc(int kind, int blk) const {
+    if (kind == dkg::PAIR_XY) return Prefetch{Y + blk * K};
+    if (kind == dkg::PAIR_XX) return Prefetch{X + blk * K};
+    if (kind == dkg::PAIR_NQ) return Prefetch{Q + blk * K};
+    return Prefetch{nullptr};
+  }
+  void prefetch_load(const Prefetch& pf, int v, uint32_t (&r)[K]) const {
+    if (pf.base) std::memcpy(r + v * VW, pf.base + v * VW, VW * 4);
+  }
   void store_q(int i, const uint32_t (&r)[K]) const { std::memcpy(Q + i * K, r, K * 4); }
   void store_x(int i, const uint32_t (&r)[K]) const { std::memcpy(X + i * K, r, K * 4); }
 };
