@@ -134,6 +134,12 @@ int dkg_jacobi_batch(int device, const uint32_t* moduli, const uint32_t* gvals, 
 int dkg_small_prime_sieve(int device, const uint32_t* moduli, const uint32_t* primes, int nprimes,
                           uint8_t* flags, size_t groups, int limbs);
 
+/* Biprimality verdict (__biprime_test_with_v_i, distributed_keygen.py:1110-1175) for the in-process
+ * case where all parties' v values are at hand: v: [parties][groups][correct][limbs], party 1
+ * first; ok[g] = 1 iff every test k < correct has v_1 = +- prod_{i>1} v_i (mod moduli[g]). */
+int dkg_biprime_verdict(int device, const uint32_t* moduli, const uint32_t* v, int parties, int correct,
+                        uint8_t* ok, size_t groups, int limbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ no CPU fallback.
 """
 from . import _native  # noqa: F401  (fails loudly if the CUDA engine is not built)
 from .engine import (  # noqa: F401
-    CombineContext, EncryptContext, ModexpContext, biprime_v_batch_limbs, jacobi_batch, launch_count,
+    CombineContext, EncryptContext, ModexpContext, biprime_v_batch_limbs, biprime_verdict, jacobi_batch, launch_count,
     modexp_grouped, modexp_grouped_limbs, small_prime_sieve,
 )
 from . import distributed_keygen  # noqa: F401

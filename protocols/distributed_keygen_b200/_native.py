@@ -33,7 +33,7 @@ EXPORTS = [
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
     "dkg_combine_batch", "dkg_combine_batch_device",
     "dkg_encrypt_batch", "dkg_modexp_grouped",
-    "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve",
+    "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve", "dkg_biprime_verdict",
 ]
 
 
@@ -74,6 +74,7 @@ def _load() -> ctypes.CDLL:
                                         c_u32p, c_void, ctypes.c_size_t, ctypes.c_int]
     lib.dkg_jacobi_batch.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_void, ctypes.c_size_t, ctypes.c_int]
     lib.dkg_small_prime_sieve.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u8p, ctypes.c_size_t, ctypes.c_int]
+    lib.dkg_biprime_verdict.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, ctypes.c_int, c_u8p, ctypes.c_size_t, ctypes.c_int]
     return lib
 
 

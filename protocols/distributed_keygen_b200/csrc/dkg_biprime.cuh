@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dkg_combine.cuh"
 #include "dkg_grouped_params_fwd.h"
 
 namespace dkg {
@@ -129,6 +130,45 @@ __global__ void clear_unused_kernel(uint32_t* out, const int* count, int limbs, 
     const unsigned long long gc = i / limbs;
     if ((int)(gc % correct) >= count[gc / correct]) out[i] = 0u;
   }
+}
+
+// Biprimality verdict (__biprime_test_with_v_i, distributed_keygen.py:1110-1175) for all
+// candidates and tests at once: test k of candidate g succeeds iff v_1 = +- prod_{i>1} v_i (mod N).
+// v: [parties][groups][correct][limbs] (party 1 first), canonical residues; ok[g] must be
+// pre-set to 1 and is cleared by any failing test.  The product is formed with word-serial
+// Montgomery multiplications without ever converting into Montgomery form: after multiplying the
+// P-1 factors the value carries R^-(P-2), and v_1 is scaled by the same power through
+// multiplications by 1, so only -N^-1 mod 2^32 is needed per candidate.
+__global__ void __launch_bounds__(64) biprime_verdict_kernel(const uint32_t* moduli, const uint32_t* v, int limbs,
+                                                             unsigned long long groups, int parties, int correct,
+                                                             uint32_t* ok) {
+  const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= groups * (unsigned long long)correct) return;
+  const unsigned long long g = idx / (unsigned long long)correct;
+  const uint32_t* n = moduli + g * (unsigned long long)limbs;
+  uint32_t n0inv = n[0];
+  for (int i = 0; i < 5; ++i) n0inv *= 2u - n[0] * n0inv;
+  n0inv = 0u - n0inv;
+  const unsigned long long party_stride = groups * (unsigned long long)correct * (unsigned long long)limbs;
+  const uint32_t* row = v + idx * (unsigned long long)limbs;
+  uint32_t x[kGroupedMaxLimbs], t1[kGroupedMaxLimbs], tmp[kGroupedMaxLimbs + 2], one[kGroupedMaxLimbs];
+  for (int l = 0; l < limbs; ++l) { t1[l] = row[l]; x[l] = parties > 1 ? row[party_stride + l] : (l == 0 ? 1u : 0u); one[l] = (l == 0) ? 1u : 0u; }
+  for (int p = 2; p < parties; ++p) {
+    gen_mont_mul(x, row + (unsigned long long)p * party_stride, 1, n, n0inv, limbs, tmp);
+    gen_mont_mul(t1, one, 1, n, n0inv, limbs, tmp);
+  }
+  // success iff x == t1 or x + t1 == N (both canonical)
+  uint32_t diff = 0;
+  uint64_t carry = 0;
+  uint32_t sumdiff = 0;
+  for (int l = 0; l < limbs; ++l) {
+    diff |= x[l] ^ t1[l];
+    const uint64_t s = (uint64_t)x[l] + t1[l] + carry;
+    sumdiff |= (uint32_t)s ^ n[l];
+    carry = s >> 32;
+  }
+  sumdiff |= (uint32_t)carry;
+  if (diff != 0 && sumdiff != 0) atomicAnd(&ok[g], 0u);
 }
 
 }  // namespace dkg

@@ -805,3 +805,36 @@ extern "C" int dkg_small_prime_sieve(int device, const uint32_t* moduli, const u
   CUDA_TRY(cudaStreamSynchronize(d->stream));
   return DKG_OK;
 }
+
+// ok[g] = 1 iff every one of the `correct` tests of candidate g satisfies v_1 = +- prod_{i>1} v_i
+extern "C" int dkg_biprime_verdict(int device, const uint32_t* moduli, const uint32_t* v, int parties, int correct,
+                                   uint8_t* ok, size_t groups, int limbs) {
+  if (!moduli || !v || !ok || parties < 1 || correct <= 0 || limbs <= 0) return fail(DKG_ERR_INVALID, "null/empty argument");
+  if (limbs > dkg::kGroupedMaxLimbs) return fail(DKG_ERR_UNSUPPORTED, "candidate wider than the biprime kernels support");
+  if (groups == 0) return DKG_OK;
+  for (size_t g = 0; g < groups; ++g)
+    if ((moduli[g * (size_t)limbs] & 1u) == 0) return fail(DKG_ERR_INVALID, "every modulus must be odd");
+  DeviceState* d = nullptr;
+  int rc = device_state(device, &d);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  DevBufs bufs;
+  uint32_t *d_mod, *d_v, *d_ok;
+  const size_t mod_b = groups * (size_t)limbs * 4, v_b = (size_t)parties * groups * correct * limbs * 4;
+  cudaError_t e = bufs.alloc(&d_mod, mod_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_v, v_b);
+  if (e == cudaSuccess) e = bufs.alloc(&d_ok, groups * 4);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("verdict cudaMalloc: ") + cudaGetErrorString(e));
+  std::vector<uint32_t> ones(groups, 1u), res(groups);
+  CUDA_TRY(cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_v, v, v_b, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_ok, ones.data(), groups * 4, cudaMemcpyHostToDevice, d->stream));
+  const unsigned long long n = groups * (unsigned long long)correct;
+  dkg::biprime_verdict_kernel<<<(unsigned)((n + 63) / 64), 64, 0, d->stream>>>(d_mod, d_v, limbs, groups, parties, correct, d_ok);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(res.data(), d_ok, groups * 4, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  for (size_t g = 0; g < groups; ++g) ok[g] = (uint8_t)(res[g] ? 1 : 0);
+  return DKG_OK;
+}

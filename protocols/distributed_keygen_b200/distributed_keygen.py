@@ -18,7 +18,7 @@ from typing import Iterable, Mapping, Sequence
 
 import numpy as np
 
-from .engine import biprime_v_batch_limbs, modexp_grouped, small_prime_sieve
+from .engine import biprime_v_batch_limbs, biprime_verdict, modexp_grouped, small_prime_sieve
 from .limbs import ints_to_limbs, limbs_for_bits, limbs_to_ints
 from .paillier_shared_key import PaillierSharedKey
 
@@ -126,6 +126,15 @@ def biprime_test_with_v_i(
         if successful >= correct_param_biprime:
             return True
     return False
+
+
+def biprime_test_with_v_i_batch(
+    v_by_party: Mapping[int, Sequence[Sequence[int]]], moduli: Sequence[int], correct_param_biprime: int,
+    device: int = 0,
+) -> list[bool]:
+    """``__biprime_test_with_v_i`` for all candidates of a round on the GPU (in-process parties):
+    ``v_by_party[i][g]`` = party i's v values for candidate g."""
+    return biprime_verdict(moduli, dict(v_by_party), correct_param_biprime, device)
 
 
 def small_prime_divisors_test_batch(prime_list: Sequence[int], moduli: Sequence[int], device: int = 0) -> list[bool]:

@@ -293,3 +293,34 @@ def small_prime_sieve(moduli: Sequence[int], primes: Sequence[int], device: int 
                                           len(moduli), limbs)
     )
     return [bool(x) for x in flags]
+
+
+def biprime_verdict(
+    moduli: Sequence[int], v_by_party: dict[int, Sequence[Sequence[int]]], correct: int, device: int = 0
+) -> list[bool]:
+    """Verdict of the biprimality test for every candidate: ``v_by_party[i][g]`` is party i's v list
+    for candidate g (party 1 is the left-hand side).  A candidate with fewer than ``correct`` v
+    values from any party fails, as do candidates with a failing test."""
+    if not moduli:
+        return []
+    groups = len(moduli)
+    parties = sorted(v_by_party)
+    if parties[0] != 1:
+        raise KeyError(1)
+    limbs = limbs_for_bits(max(m.bit_length() for m in moduli))
+    enough = [all(len(v_by_party[p][g]) >= correct for p in parties) for g in range(groups)]
+    arr = np.zeros((len(parties), groups, correct, limbs), dtype=np.uint32)
+    for pi, p in enumerate(parties):
+        flat = []
+        for g in range(groups):
+            vs = list(v_by_party[p][g][:correct]) if enough[g] else []
+            flat.extend(x % moduli[g] for x in vs)
+            flat.extend([0] * (correct - len(vs)))
+        arr[pi] = ints_to_limbs(flat, limbs).reshape(groups, correct, limbs)
+    ok = np.zeros(groups, dtype=np.uint8)
+    m_arr = ints_to_limbs(moduli, limbs)
+    _native.check(
+        _native.lib.dkg_biprime_verdict(device, m_arr.ctypes.data, arr.ctypes.data, len(parties), correct,
+                                        ok.ctypes.data, groups, limbs)
+    )
+    return [bool(o) and e for o, e in zip(ok, enough)]

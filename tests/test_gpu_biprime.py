@@ -116,3 +116,44 @@ def test_biprime_round_fused_many_candidates():
         got = dkg.biprime_test_v_calculation_batch(batch, party, correct)
         want = [po.biprime_v_calculation(gs, party, n, p_i, q_i, correct) for (gs, n, p_i, q_i) in batch]
         assert got == want
+
+
+def test_biprime_verdict_on_gpu(biprime_vectors):
+    """Verdicts for the recorded reference candidates (real biprimes pass, the others fail), and a
+    full in-process round: v values of all parties from the GPU, verdict on the GPU."""
+    from oracle import keys as okeys
+    from oracle import paillier_oracle as po
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+
+    for correct in sorted({c["correct_param_biprime"] for c in biprime_vectors["cases"]}):
+        for parties in (3, 4, 5):
+            cases = [c for c in biprime_vectors["cases"] if c["correct_param_biprime"] == correct and c["parties"] == parties]
+            cases = [c for c in cases if all(len(v) >= correct for v in c["v"].values())]
+            if not cases:
+                continue
+            moduli = [_h(c["n"]) for c in cases]
+            v_by_party = {p: [[_h(x) for x in c["v"][str(p)]] for c in cases] for p in range(1, parties + 1)}
+            assert dkg.biprime_test_with_v_i_batch(v_by_party, moduli, correct) == [c["verdict"] for c in cases]
+    rng = random.Random(77)
+    pl, correct = 64, 20
+    cands = []
+    want_bp = [True, False, True, False, False, True]
+    for bp in want_bp:
+        while True:
+            p_sh = [okeys.prime_candidate_share(i + 1, pl, rng) for i in range(3)]
+            q_sh = [okeys.prime_candidate_share(i + 1, pl, rng) for i in range(3)]
+            is_bp = okeys._is_probable_prime(sum(p_sh), rng) and okeys._is_probable_prime(sum(q_sh), rng)
+            if is_bp == bp:
+                break
+        n = sum(p_sh) * sum(q_sh)
+        cands.append(([rng.randint(0, n) % n for _ in range(correct * 4)], n, p_sh, q_sh))
+    v_by_party = {}
+    for party in (1, 2, 3):
+        batch = [(gs, n, p_sh[party - 1], q_sh[party - 1]) for (gs, n, p_sh, q_sh) in cands]
+        v_by_party[party] = dkg.biprime_test_v_calculation_batch(batch, party, correct)
+    got = dkg.biprime_test_with_v_i_batch(v_by_party, [c[1] for c in cands], correct)
+    want = [po.biprime_verdict({p: v_by_party[p][g] for p in v_by_party}, cands[g][1], correct) for g in range(len(cands))]
+    assert got == want == want_bp
+    # a candidate with too few usable g's fails
+    short = {p: [v_by_party[p][0][:5]] for p in v_by_party}
+    assert dkg.biprime_test_with_v_i_batch(short, [cands[0][1]], correct) == [False]
