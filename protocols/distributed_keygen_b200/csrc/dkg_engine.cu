@@ -97,6 +97,7 @@ struct DeviceState {
   unsigned int* counter = nullptr;
   uint32_t* aux = nullptr;  // batched-inversion buffers
   size_t aux_words = 0;
+  std::mutex mu;            // serialises the synchronous host-buffer entry points on this device
 };
 std::mutex g_dev_mu;
 DeviceState g_devs[16];
@@ -113,6 +114,13 @@ int device_state(int device, DeviceState** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&d.counter, sizeof(unsigned int)));
+    // batch buffers of the host-buffer entry points come from the stream-ordered pool and stay
+    // cached there between calls (no cudaMalloc/cudaFree on the data path)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     d.device = device;
   }
   *out = &d;
@@ -133,6 +141,20 @@ int ensure_scratch(DeviceState* d, size_t words) {
   d->scratch_words = words;
   return DKG_OK;
 }
+
+struct DevBufs {
+  cudaStream_t stream = nullptr;
+  std::vector<void*> ptrs;
+  explicit DevBufs(cudaStream_t s) : stream(s) {}
+  ~DevBufs() { for (void* p : ptrs) if (p) cudaFreeAsync(p, stream); }
+  template <typename T> cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T*)p;
+    return e;
+  }
+};
 
 int ensure_aux(DeviceState* d, size_t words) {
   if (d->aux_words >= words) return DKG_OK;
@@ -364,29 +386,22 @@ int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, 
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   const size_t bytes = count * (size_t)ctx->limbs * 4;
-  uint32_t *d_in = nullptr, *d_out = nullptr;
-  uint8_t* d_st = nullptr;
-  cudaError_t e = cudaMalloc(&d_in, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_st, count);
-  int rc = DKG_OK;
-  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("batch cudaMalloc: ") + cudaGetErrorString(e));
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(d_in, bases, bytes, cudaMemcpyHostToDevice, d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
-  }
-  if (rc == DKG_OK) rc = launch_modexp(ctx, d_in, d_out, d_st, nullptr, count, d->stream);
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_st, count, cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("modexp batch: ") + cudaGetErrorString(e));
-  }
-  if (d_in) cudaFree(d_in);
-  if (d_out) cudaFree(d_out);
-  if (d_st) cudaFree(d_st);
-  return rc;
+  uint32_t *d_in, *d_out;
+  uint8_t* d_st;
+  cudaError_t e = bufs.alloc(&d_in, bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_out, bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_st, count);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("batch alloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_in, bases, bytes, cudaMemcpyHostToDevice, d->stream));
+  int rc = launch_modexp(ctx, d_in, d_out, d_st, nullptr, count, d->stream);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, d->stream));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_st, count, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
 }
 
 // ---- not yet implemented entry points ------------------------------------------------------------
@@ -494,29 +509,22 @@ int dkg_combine_batch(dkg_combine_ctx* ctx, const uint32_t* partials, uint32_t* 
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   const size_t in_bytes = (size_t)ctx->shares * count * ctx->l2 * 4, out_bytes = count * (size_t)ctx->ln * 4;
-  uint32_t *d_in = nullptr, *d_out = nullptr;
-  uint8_t* d_st = nullptr;
-  cudaError_t e = cudaMalloc(&d_in, in_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_st, count);
-  int rc = DKG_OK;
-  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("combine cudaMalloc: ") + cudaGetErrorString(e));
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(d_in, partials, in_bytes, cudaMemcpyHostToDevice, d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
-  }
-  if (rc == DKG_OK) rc = launch_combine(ctx, d_in, d_out, d_st, count, d->stream);
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_st, count, cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("combine batch: ") + cudaGetErrorString(e));
-  }
-  if (d_in) cudaFree(d_in);
-  if (d_out) cudaFree(d_out);
-  if (d_st) cudaFree(d_st);
-  return rc;
+  uint32_t *d_in, *d_out;
+  uint8_t* d_st;
+  cudaError_t e = bufs.alloc(&d_in, in_bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_out, out_bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_st, count);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("combine alloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_in, partials, in_bytes, cudaMemcpyHostToDevice, d->stream));
+  int rc = launch_combine(ctx, d_in, d_out, d_st, count, d->stream);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_st, count, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
 }
 
 }  // extern "C"
@@ -531,41 +539,32 @@ extern "C" int dkg_encrypt_batch(dkg_modexp_ctx* ctx, const uint32_t* n, int n_l
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
   const size_t in_bytes = count * (size_t)n_limbs * 4, out_bytes = count * (size_t)ctx->limbs * 4;
-  uint32_t *d_r = nullptr, *d_m = nullptr, *d_n = nullptr, *d_base = nullptr, *d_fm = nullptr, *d_out = nullptr;
-  int rc = DKG_OK;
-  cudaError_t e = cudaMalloc(&d_r, in_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_base, out_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_n, (size_t)n_limbs * 4);
-  if (e == cudaSuccess && m) e = cudaMalloc(&d_m, in_bytes);
-  if (e == cudaSuccess && m) e = cudaMalloc(&d_fm, out_bytes);
-  if (e != cudaSuccess) rc = fail(DKG_ERR_NOMEM, std::string("encrypt cudaMalloc: ") + cudaGetErrorString(e));
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(d_r, r, in_bytes, cudaMemcpyHostToDevice, d->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, n, (size_t)n_limbs * 4, cudaMemcpyHostToDevice, d->stream);
-    if (e == cudaSuccess && m) e = cudaMemcpyAsync(d_m, m, in_bytes, cudaMemcpyHostToDevice, d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
-  }
-  if (rc == DKG_OK) {
-    const unsigned blocks = (unsigned)std::min<size_t>((count * ctx->limbs + 255) / 256, 148 * 16);
-    dkg::pad_rows_kernel<<<blocks, 256, 0, d->stream>>>(d_r, n_limbs, d_base, ctx->limbs, count);
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
+  uint32_t *d_r, *d_m = nullptr, *d_n, *d_base, *d_fm = nullptr, *d_out;
+  cudaError_t e = bufs.alloc(&d_r, in_bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_base, out_bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_out, out_bytes);
+  if (e == cudaSuccess) e = bufs.alloc(&d_n, (size_t)n_limbs * 4);
+  if (e == cudaSuccess && m) e = bufs.alloc(&d_m, in_bytes);
+  if (e == cudaSuccess && m) e = bufs.alloc(&d_fm, out_bytes);
+  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("encrypt alloc: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_r, r, in_bytes, cudaMemcpyHostToDevice, d->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_n, n, (size_t)n_limbs * 4, cudaMemcpyHostToDevice, d->stream));
+  if (m) CUDA_TRY(cudaMemcpyAsync(d_m, m, in_bytes, cudaMemcpyHostToDevice, d->stream));
+  const unsigned blocks = (unsigned)std::min<size_t>((count * ctx->limbs + 255) / 256, 148 * 16);
+  dkg::pad_rows_kernel<<<blocks, 256, 0, d->stream>>>(d_r, n_limbs, d_base, ctx->limbs, count);
+  g_launches.fetch_add(1);
+  if (m) {
+    dkg::one_plus_mn_kernel<<<(unsigned)((count + 127) / 128), 128, 0, d->stream>>>(d_m, d_n, n_limbs, d_fm, ctx->limbs, count);
     g_launches.fetch_add(1);
-    if (m) {
-      dkg::one_plus_mn_kernel<<<(unsigned)((count + 127) / 128), 128, 0, d->stream>>>(d_m, d_n, n_limbs, d_fm, ctx->limbs, count);
-      g_launches.fetch_add(1);
-    }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, cudaGetErrorString(e));
   }
-  if (rc == DKG_OK) rc = launch_modexp(ctx, d_base, d_out, nullptr, m ? d_fm : nullptr, count, d->stream);
-  if (rc == DKG_OK) {
-    e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
-    if (e != cudaSuccess) rc = fail(DKG_ERR_CUDA, std::string("encrypt batch: ") + cudaGetErrorString(e));
-  }
-  for (uint32_t* ptr : {d_r, d_m, d_n, d_base, d_fm, d_out})
-    if (ptr) cudaFree(ptr);
-  return rc;
+  CUDA_TRY(cudaGetLastError());
+  int rc = launch_modexp(ctx, d_base, d_out, nullptr, m ? d_fm : nullptr, count, d->stream);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return DKG_OK;
 }
 
 // ---- grouped modexp (biprimality test batch) -------------------------------------------------------
@@ -631,17 +630,6 @@ int launch_grouped(DeviceState* d, const GroupedPlan& plan, const uint32_t* d_mo
   return DKG_OK;
 }
 
-struct DevBufs {
-  std::vector<void*> ptrs;
-  ~DevBufs() { for (void* p : ptrs) if (p) cudaFree(p); }
-  template <typename T> cudaError_t alloc(T** out, size_t bytes) {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    if (e == cudaSuccess) ptrs.push_back(p);
-    *out = (T*)p;
-    return e;
-  }
-};
 
 }  // namespace
 
@@ -662,7 +650,8 @@ extern "C" int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint
   GroupedPlan plan;
   rc = plan_grouped(d, limbs, ebits, count, &plan);
   if (rc != DKG_OK) return rc;
-  DevBufs bufs;
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_exp, *d_bases, *d_out, *d_gc;
   uint8_t* d_dig;
   const size_t mod_b = groups * (size_t)limbs * 4, exp_b = groups * (size_t)exp_limbs * 4, base_b = count * (size_t)limbs * 4;
@@ -704,7 +693,8 @@ extern "C" int dkg_biprime_v_batch(int device, const uint32_t* moduli, const uin
   GroupedPlan plan;
   rc = plan_grouped(d, limbs, ebits, count, &plan);
   if (rc != DKG_OK) return rc;
-  DevBufs bufs;
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_exp, *d_g, *d_bases, *d_out, *d_gc;
   uint8_t* d_dig;
   int8_t* d_sym;
@@ -755,7 +745,8 @@ extern "C" int dkg_jacobi_batch(int device, const uint32_t* moduli, const uint32
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  DevBufs bufs;
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_g;
   int8_t* d_sym;
   const size_t mod_b = groups * (size_t)limbs * 4, g_b = groups * (size_t)per_group * limbs * 4;
@@ -785,7 +776,8 @@ extern "C" int dkg_small_prime_sieve(int device, const uint32_t* moduli, const u
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  DevBufs bufs;
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_pr;
   uint8_t* d_fl;
   const size_t mod_b = groups * (size_t)limbs * 4;
@@ -818,7 +810,8 @@ extern "C" int dkg_biprime_verdict(int device, const uint32_t* moduli, const uin
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  DevBufs bufs;
+  std::lock_guard<std::mutex> lk(d->mu);
+  DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_v, *d_ok;
   const size_t mod_b = groups * (size_t)limbs * 4, v_b = (size_t)parties * groups * correct * limbs * 4;
   cudaError_t e = bufs.alloc(&d_mod, mod_b);

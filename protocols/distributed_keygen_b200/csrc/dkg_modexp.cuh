@@ -55,14 +55,16 @@ __device__ __forceinline__ void ldg_vec(uint2& v, const uint2* p) {
   asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
 }
 
-// predicated generic loads (the register keeps its value when the predicate is off)
-__device__ __forceinline__ void ld_generic_pred(uint32_t* r, const char* p, uint32_t on, uint4) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"(on) : "memory");
+// two predicated loads (global / shared); the registers keep their value when both are off
+__device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t on_g, uint32_t sp, uint32_t on_s, uint4) {
+  asm volatile("{\n\t.reg .pred pg, ps;\n\tsetp.ne.u32 pg, %5, 0;\n\tsetp.ne.u32 ps, %7, 0;\n\t"
+               "@pg ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t@ps ld.shared.v4.u32 {%0, %1, %2, %3}, [%6];\n\t}"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(gp), "r"(on_g), "r"(sp), "r"(on_s) : "memory");
 }
-__device__ __forceinline__ void ld_generic_pred(uint32_t* r, const char* p, uint32_t on, uint2) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.v2.u32 {%0, %1}, [%2];\n\t}"
-               : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"(on) : "memory");
+__device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t on_g, uint32_t sp, uint32_t on_s, uint2) {
+  asm volatile("{\n\t.reg .pred pg, ps;\n\tsetp.ne.u32 pg, %3, 0;\n\tsetp.ne.u32 ps, %5, 0;\n\t"
+               "@pg ld.global.v2.u32 {%0, %1}, [%2];\n\t@ps ld.shared.v2.u32 {%0, %1}, [%4];\n\t}"
+               : "+r"(r[0]), "+r"(r[1]) : "l"(gp), "r"(on_g), "r"(sp), "r"(on_s) : "memory");
 }
 
 // IO policy of dkg::mont_mul for one thread of a warp.
@@ -97,22 +99,23 @@ struct WarpIO {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Qg + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
   }
-  // Prefetch descriptor: generic address of vector 0 of the block, byte stride between vectors,
-  // and an on/off flag.  X blocks are addressed through the generic window of shared memory so
-  // that one predicated generic load serves all three sources.
-  struct Prefetch { const char* base; uint32_t stride; uint32_t on; };
+  // Prefetch descriptor: the next y operand comes either from shared memory (an X block) or from
+  // global memory (table entry / quotient block).  Two predicated loads, exactly one of which is
+  // on, keep the block product branch-free without going through generic addressing.
+  struct Prefetch { const char* gbase; uint32_t gstride; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
-    d.on = (kind == PAIR_XY || kind == PAIR_XX || kind == PAIR_NQ) ? 1u : 0u;
-    const char* xg = reinterpret_cast<const char*>(__cvta_shared_to_generic((size_t)xs)) + (size_t)(blk * KV) * 32u * VB;
+    d.on_s = (kind == PAIR_XX) ? 1u : 0u;
+    d.on_g = (kind == PAIR_XY || kind == PAIR_NQ) ? 1u : 0u;
+    d.sbase = xs + (uint32_t)(blk * KV) * 32u * VB;
     const char* yg = reinterpret_cast<const char*>(Y + (size_t)(blk * KV) * ystride);
     const char* qg = reinterpret_cast<const char*>(Qg + (size_t)(blk * KV) * 32);
-    d.base = kind == PAIR_XY ? yg : (kind == PAIR_XX ? xg : qg);
-    d.stride = kind == PAIR_XY ? (uint32_t)ystride * VB : 32u * VB;
+    d.gbase = kind == PAIR_XY ? yg : qg;
+    d.gstride = kind == PAIR_XY ? (uint32_t)ystride * VB : 32u * VB;
     return d;
   }
   __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
-    ld_generic_pred(&r[v * VW], d.base + (size_t)v * d.stride, d.on, V());
+    ld_pred2(&r[v * VW], d.gbase + (size_t)v * d.gstride, d.on_g, d.sbase + (uint32_t)v * 32u * VB, d.on_s, V());
   }
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
 #pragma unroll
