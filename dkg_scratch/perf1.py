@@ -10,10 +10,10 @@ for name in sys.argv[1:] or ['cfg2_k2048_p3_t1_exact']:
     dk = okeys.dealer_key_from_json(dv['keys'][name]['key'])
     for pid, key in dk.keys.items():
         e = key.partial_decrypt_exponent()
-        ctx = eng.ModexpContext(key.n_square, e)
+        ctx = eng.ModexpContext(key.n_square, e, root=(key.n if not __import__('os').environ.get('NOROOT') else None))
         info = ctx.info()
         per_wave = info['ctas'] * info['warps_per_cta'] * 32
-        for B in [per_wave, 2 * per_wave]:
+        for B in [per_wave, 4 * per_wave]:
             rng = np.random.default_rng(1)
             host = rng.integers(0, 2**32, size=(B, ctx.limbs), dtype=np.uint32)
             host[:, -1] &= (1 << ((key.n_square.bit_length() - 1) % 32)) - 1 if key.n_square.bit_length() % 32 else 0x7fffffff

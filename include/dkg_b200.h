@@ -78,10 +78,17 @@ int dkg_measure_imad_peak(int device, double* plain_wide_mac_per_s, double* carr
 int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs,
                           const uint32_t* exponent, int exp_limbs, int exp_negative,
                           dkg_modexp_ctx** out);
+/* Same, for the modulus N^2 given its root n (the Paillier case: partial decryption and encryption
+ * randomness work modulo N^2 with N public).  Rows are values modulo N^2 (limbs of N^2, see
+ * dkg_modexp_ctx_info / the caller's own count); results are identical to the generic context,
+ * the exponentiation runs in pair arithmetic modulo N (csrc/dkg_nsq.cuh). */
+int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const uint32_t* exponent,
+                              int exp_limbs, int exp_negative, dkg_modexp_ctx** out);
 void dkg_modexp_ctx_destroy(dkg_modexp_ctx* ctx);
 /* info[0]=K, [1]=M, [2]=padded limbs, [3]=window bits, [4]=windows, [5]=exponent bits,
- * [6]=warps per CTA, [7]=CTAs */
-int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[8]);
+ * [6]=warps per CTA, [7]=CTAs, [8]=1 if the pair arithmetic modulo the root is active,
+ * [9]=its K, [10]=its M, [11]=its warps per CTA */
+int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[12]);
 
 /* out[i] = bases[i] ^ (+-exponent) mod modulus; rows of mod_limbs limbs.  Host buffers. */
 int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, uint8_t* status,

@@ -28,7 +28,7 @@ STATUS_NOT_DIVISIBLE = 2
 EXPORTS = [
     "dkg_version", "dkg_last_error", "dkg_device_count", "dkg_launch_count",
     "dkg_measure_imad_peak",
-    "dkg_modexp_ctx_create", "dkg_modexp_ctx_destroy", "dkg_modexp_ctx_info",
+    "dkg_modexp_ctx_create", "dkg_modexp_ctx_create_nsq", "dkg_modexp_ctx_destroy", "dkg_modexp_ctx_info",
     "dkg_modexp_batch", "dkg_modexp_batch_device",
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
     "dkg_combine_batch", "dkg_combine_batch_device",
@@ -57,9 +57,10 @@ def _load() -> ctypes.CDLL:
     lib.dkg_launch_count.restype = ctypes.c_ulonglong
     lib.dkg_measure_imad_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.dkg_modexp_ctx_create.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void)]
+    lib.dkg_modexp_ctx_create_nsq.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void)]
     lib.dkg_modexp_ctx_destroy.argtypes = [c_void]
     lib.dkg_modexp_ctx_destroy.restype = None
-    lib.dkg_modexp_ctx_info.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 8)]
+    lib.dkg_modexp_ctx_info.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 12)]
     lib.dkg_modexp_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_modexp_batch_device.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t, c_void]
     lib.dkg_combine_ctx_create.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.POINTER(c_void)]

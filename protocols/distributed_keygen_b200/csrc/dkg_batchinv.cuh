@@ -39,8 +39,11 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
   const V* R3g = reinterpret_cast<const V*>(p.consts + Lp + K + 2 * Lp);
   V* Qg = reinterpret_cast<V*>(p.scratch + (size_t)w * Lp * 32);
 
-  WarpIO<K, M> ioX{(uint32_t)__cvta_generic_to_shared(Xw + lane), (uint32_t)__cvta_generic_to_shared(Ns),
-                   (uint32_t)__cvta_generic_to_shared(NIs), Qg + lane, nullptr, 0};
+  WarpIO<K, M> ioX;
+  ioX.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
+  ioX.ns = (uint32_t)__cvta_generic_to_shared(Ns);
+  ioX.nis = (uint32_t)__cvta_generic_to_shared(NIs);
+  ioX.Qg = Qg + lane; ioX.Y = nullptr; ioX.ystride = 0;
   WarpIO<K, M> ioX2 = ioX;
   ioX2.xs = (uint32_t)__cvta_generic_to_shared(X2w + lane);
 
@@ -89,6 +92,21 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
   ioX.Y = R3g; ioX.ystride = 1;
   mont_call<K, M, MONT_MUL>(ioX);
   p.chain_status[(size_t)w * 32 + lane] = bad;
+  if (bad && p.any_bad != nullptr) atomicOr(p.any_bad, 1u);
+
+  // optional: canonical plain inverse of the group held in `io`'s X, written as rows
+  auto store_plain = [&](WarpIO<K, M>& io, uint32_t* x32, unsigned long long g) {
+    mont_call<K, M, MONT_REDC>(io);
+    canonicalize<K, M>(io, 1);
+    __syncwarp();
+    const unsigned long long first = g * 32ull;
+    const int cnt = (int)((p.count - first) < 32ull ? (p.count - first) : 32ull);
+    for (int r = 0; r < cnt; ++r) {
+      uint32_t* row = p.plain_out + (first + (unsigned long long)r) * (unsigned long long)p.in_limbs;
+      for (int l = lane; l < p.in_limbs; l += 32) row[l] = x32[((l / VW) * 32 + r) * VW + (l % VW)];
+    }
+    __syncwarp();
+  };
 
   // ---- phase C: peel the chain from the back ------------------------------------------------------
   // inv = (c_0 .. c_k)^-1 ; c_k^-1 = inv * P_{k-1} ; inv <- inv * c_k
@@ -101,10 +119,12 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
     ioX.Y = s; ioX.ystride = 32;
     mont_call<K, M, MONT_MUL>(ioX);                      // inv for the next step
     for (int v = 0; v < LV; ++v) s[(size_t)v * 32] = X2w[v * 32 + lane];
+    if (p.plain_out != nullptr) store_plain(ioX2, X2w32, g);
   }
   {
     V* s = S(group_of(0));
     for (int v = 0; v < LV; ++v) s[(size_t)v * 32] = Xw[v * 32 + lane];
+    if (p.plain_out != nullptr) store_plain(ioX, reinterpret_cast<uint32_t*>(Xw), group_of(0));
   }
 }
 

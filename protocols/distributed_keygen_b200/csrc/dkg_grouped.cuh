@@ -113,8 +113,11 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
   V* R2l = Qg + LV * 32;    // this warp's lanes' R^2 mod N, lane layout
   V* ONEl = R2l + LV * 32;  // and R mod N
 
-  WarpIO<K, M, true> io{(uint32_t)__cvta_generic_to_shared(Xw + lane), (uint32_t)__cvta_generic_to_shared(Nw + lane),
-                        (uint32_t)__cvta_generic_to_shared(NIw + lane), Qg + lane, nullptr, 0};
+  WarpIO<K, M, true> io;
+  io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
+  io.ns = (uint32_t)__cvta_generic_to_shared(Nw + lane);
+  io.nis = (uint32_t)__cvta_generic_to_shared(NIw + lane);
+  io.Qg = Qg + lane; io.Y = nullptr; io.ystride = 0;
 
   const unsigned long long count = p.groups * (unsigned long long)p.per_group;
   const unsigned long long nwork = (count + 31ull) / 32ull;

@@ -111,4 +111,25 @@ inline Limbs mulmod_slow(const Limbs& a, const Limbs& b, const Limbs& n) {
   return r;
 }
 
+// a = q * n + r by bit-serial long division (a: any length, n: n.size() limbs, n > 0);
+// q has a.size() limbs, r has n.size() limbs.  One-off constants only.
+inline void divmod_slow(const Limbs& a, const Limbs& n, Limbs* q, Limbs* r) {
+  const size_t len = n.size();
+  q->assign(a.size(), 0);
+  r->assign(len, 0);
+  const int abits = bit_length(a.data(), (int)a.size());
+  for (int k = abits - 1; k >= 0; --k) {
+    uint32_t carry = (a[k / 32] >> (k % 32)) & 1u;
+    for (size_t i = 0; i < len; ++i) {
+      const uint32_t nc = (*r)[i] >> 31;
+      (*r)[i] = ((*r)[i] << 1) | carry;
+      carry = nc;
+    }
+    if (carry || geq(*r, n)) {
+      sub_inplace(*r, n);
+      (*q)[k / 32] |= 1u << (k % 32);
+    }
+  }
+}
+
 }  // namespace dkg_host

@@ -86,10 +86,17 @@ struct WarpIO {
   V* Qg;
   const V* Y;
   int ystride;
+  uint32_t ss = 0;          // second shared-memory operand S (pair arithmetic), lane's vector 0
+  const V* Y2 = nullptr;    // second global operand
+  int y2stride = 0;
 
   __device__ __forceinline__ void load_x(int i, uint32_t (&r)[K]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, xs + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
+  }
+  __device__ __forceinline__ void load_s(int i, uint32_t (&r)[K]) const {
+#pragma unroll
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, ss + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_y(int j, uint32_t (&r)[K]) const {
 #pragma unroll
@@ -105,13 +112,14 @@ struct WarpIO {
   struct Prefetch { const char* gbase; uint32_t gstride; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
-    d.on_s = (kind == PAIR_XX) ? 1u : 0u;
-    d.on_g = (kind == PAIR_XY || kind == PAIR_NQ) ? 1u : 0u;
-    d.sbase = xs + (uint32_t)(blk * KV) * 32u * VB;
+    d.on_s = (kind == PAIR_XX || kind == PAIR_XS) ? 1u : 0u;
+    d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
+    d.sbase = (kind == PAIR_XS ? ss : xs) + (uint32_t)(blk * KV) * 32u * VB;
     const char* yg = reinterpret_cast<const char*>(Y + (size_t)(blk * KV) * ystride);
+    const char* y2g = reinterpret_cast<const char*>(Y2 + (size_t)(blk * KV) * y2stride);
     const char* qg = reinterpret_cast<const char*>(Qg + (size_t)(blk * KV) * 32);
-    d.gbase = kind == PAIR_XY ? yg : qg;
-    d.gstride = kind == PAIR_XY ? (uint32_t)ystride * VB : 32u * VB;
+    d.gbase = kind == PAIR_XY ? yg : (kind == PAIR_SY2 ? y2g : qg);
+    d.gstride = kind == PAIR_XY ? (uint32_t)ystride * VB : (kind == PAIR_SY2 ? (uint32_t)y2stride * VB : 32u * VB);
     return d;
   }
   __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
@@ -233,12 +241,15 @@ __device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n
   return bad;
 }
 
-// Out-of-line instances of the Montgomery product: the kernel body calls these (three function
-// bodies per shape: square, multiply-by-global-operand, reduce) instead of inlining seven copies,
-// which keeps the hot loop inside the instruction cache.
+// One out-of-line instance of the Montgomery product per shape, shared by every mode (square,
+// multiply, reduce, doubled product, multiply-add): the hot loop stays inside the instruction cache.
+template <int K, int M, bool PLN>
+__device__ __noinline__ void mont_call_rt(const WarpIO<K, M, PLN> io, const int mode) {
+  mont_mul<K, M>(io, mode);
+}
 template <int K, int M, int MODE, bool PLN = false>
-__device__ __noinline__ void mont_call(const WarpIO<K, M, PLN> io) {
-  mont_mul<K, M, MODE>(io);
+__device__ __forceinline__ void mont_call(const WarpIO<K, M, PLN>& io) {
+  mont_call_rt<K, M, PLN>(io, MODE);
 }
 
 template <int K, int M>
@@ -268,8 +279,11 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
   V* tab = reinterpret_cast<V*>(scratch32);  // entry d (1-based) at tab[((d-1)*LV + v)*32 + lane]
   V* Qg = reinterpret_cast<V*>(scratch32 + p.scratch_q_offset);  // quotient blocks, [v*32 + lane]
 
-  WarpIO<K, M> io{(uint32_t)__cvta_generic_to_shared(Xw + lane), (uint32_t)__cvta_generic_to_shared(Ns),
-                  (uint32_t)__cvta_generic_to_shared(NIs), Qg + lane, nullptr, 0};
+  WarpIO<K, M> io;
+  io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
+  io.ns = (uint32_t)__cvta_generic_to_shared(Ns);
+  io.nis = (uint32_t)__cvta_generic_to_shared(NIs);
+  io.Qg = Qg + lane; io.Y = nullptr; io.ystride = 0;
 
   const unsigned long long ngroups = (p.count + 31ull) / 32ull;
   for (;;) {

@@ -51,6 +51,8 @@ struct BatchInvParams {
   uint32_t* scratch;       // per-warp quotient-block scratch, [warps][Lp*32]
   int nchain_warps;
   int chain_len;           // groups per chain warp (upper bound)
+  uint32_t* plain_out;     // optional [count][in_limbs]: canonical c^-1 mod N (rows), else null
+  unsigned int* any_bad;   // set to 1 if any chain was not invertible
 };
 
 }  // namespace dkg

@@ -22,7 +22,10 @@
 
 namespace dkg {
 
-enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2 };
+// MONT_MUL2S / MONT_MULADD serve the pair arithmetic modulo N^2 (dkg_nsq.cuh):
+//   MUL2S : X <- 2 * X * S * R^-1      (S = second shared-memory operand, products doubled)
+//   MULADD: X <- (X * Y + S * Y2) * R^-1   (Y, Y2 in global memory)
+enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2, MONT_MUL2S = 3, MONT_MULADD = 4 };
 
 // Column accumulator of the block product scan, kept in a carry-save form so that a K x K block
 // multiply-accumulate is nothing but IMAD.WIDE carry chains:
@@ -54,7 +57,9 @@ DKG_HD void acc_clear_side(ColAcc<K>& a) {
 //   PAIR_XX: x = X_i, y = X_j (shared; squaring)
 //   PAIR_NQ: x = N_i (shared, CTA-uniform), y = Q_j (global scratch, written earlier by this thread)
 //   PAIR_QC: the quotient step (x = Q_c fresh in registers, y = N_0)
-enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4 };
+//   PAIR_XS: x = X_i, y = S_j (second shared-memory operand)
+//   PAIR_SY2: x = S_i, y = Y2_j (second global operand)
+enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4, PAIR_XS = 5, PAIR_SY2 = 6 };
 
 struct PairDesc {
   int kind, xi, yi;
@@ -158,38 +163,45 @@ DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32
 }
 
 // Pair schedule of column c of the block product scan.
-template <int M, int MODE>
+template <int M>
 struct ColPlan {
-  int lo, nxy, ncross, nq, total;
-  DKG_HD explicit ColPlan(int c) {
+  int lo, span, nxy, ndouble, nq, total, MODE;
+  DKG_HD ColPlan(int c, int mode) {
+    MODE = mode;
     lo = c >= M ? c - M + 1 : 0;
     const int hi = c < M ? c : M - 1;
-    const int span = hi - lo + 1;                     // X_i * Y_{c-i}, i in [lo, hi]
+    span = hi - lo + 1;                               // X_i * Y_{c-i}, i in [lo, hi]
     // squaring: pairs i < c-i once (doubled afterwards), the middle i == c-i once more
-    ncross = (MODE == MONT_SQR) ? span / 2 : 0;
-    nxy = (MODE == MONT_MUL) ? span : (MODE == MONT_SQR ? ncross + (span & 1) : 0);
+    ndouble = (MODE == MONT_SQR) ? span / 2 : (MODE == MONT_MUL2S ? span : 0);
+    nxy = (MODE == MONT_MUL || MODE == MONT_MUL2S) ? span
+          : (MODE == MONT_SQR ? span / 2 + (span & 1) : (MODE == MONT_MULADD ? 2 * span : 0));
     nq = (c < M ? c - 1 : M - 1) - lo + 1;            // Q_i * N_{c-i}, i in [lo, ..]
     total = nxy + nq + (c < M ? 1 : 0);               // + the quotient step
   }
-  // squaring: cross products, (double), middle square, N*Q products, quotient step
-  // multiplication / reduction: N*Q products, X*Y products, quotient step
+  // squaring / doubled product: operand products (the leading `ndouble` are doubled), N*Q
+  //   products, quotient step
+  // multiplication / multiply-add / reduction: N*Q products, operand products, quotient step
   DKG_HD PairDesc at(int c, int t) const {
     PairDesc d;
-    if (MODE == MONT_SQR) {
-      if (t < nxy) { d.kind = PAIR_XX; d.xi = lo + t; d.yi = c - d.xi; }
+    d.xi = 0; d.yi = 0;
+    if (MODE == MONT_SQR || MODE == MONT_MUL2S) {
+      if (t < nxy) { d.kind = (MODE == MONT_SQR) ? PAIR_XX : PAIR_XS; d.xi = lo + t; d.yi = c - d.xi; }
       else if (t < nxy + nq) { d.kind = PAIR_NQ; d.yi = lo + (t - nxy); d.xi = c - d.yi; }
-      else { d.kind = PAIR_QC; d.xi = 0; d.yi = 0; }
+      else d.kind = PAIR_QC;
     } else {
       if (t < nq) { d.kind = PAIR_NQ; d.yi = lo + t; d.xi = c - d.yi; }
-      else if (t < nq + nxy) { d.kind = PAIR_XY; d.xi = lo + (t - nq); d.yi = c - d.xi; }
-      else { d.kind = PAIR_QC; d.xi = 0; d.yi = 0; }
+      else if (t < nq + nxy) {
+        const int u = t - nq;
+        if (MODE == MONT_MULADD && u >= span) { d.kind = PAIR_SY2; d.xi = lo + (u - span); d.yi = c - d.xi; }
+        else { d.kind = PAIR_XY; d.xi = lo + u; d.yi = c - d.xi; }
+      } else d.kind = PAIR_QC;
     }
     return d;
   }
 };
 
 // IO policy (all indices are block indices; r has K limbs; VW = limbs per vector):
-//   load_x(i, r)  load_y(j, r)  load_q(i, r)  load_n(j, r)  load_ninv(r)
+//   load_x(i, r)  load_s(i, r)  load_y(j, r)  load_q(i, r)  load_n(j, r)  load_ninv(r)
 //   prefetch_desc(kind, block) -> IO::Prefetch ; prefetch_load(desc, v, r)   (vector v of the block)
 //   store_q(i, r) store_x(i, r)
 //
@@ -197,8 +209,11 @@ struct ColPlan {
 // MONT_SQR : X <- X * X * R^-1 mod N   (cross block products computed once and doubled)
 // MONT_REDC: X <- X * R^-1 mod N
 // Result in [0, R); X is overwritten block by block (block c-M is dead when column c starts).
-template <int K, int M, int MODE, class IO>
-DKG_HD void mont_mul(const IO& io) {
+// `MODE` is a run-time (warp-uniform) argument on purpose: all modes share ONE instance of the
+// unrolled block product, so the hot loop of an exponentiation (squarings, multiplications and, in
+// the pair arithmetic, the two mixed products) stays inside the instruction cache.
+template <int K, int M, class IO>
+DKG_HD void mont_mul(const IO& io, const int MODE) {
   ColAcc<K> a;
   uint32_t Tc[K + 2];  // carry-in from the previous column (merged)
 #pragma unroll
@@ -210,14 +225,15 @@ DKG_HD void mont_mul(const IO& io) {
   uint32_t xb[K], yb[K];
   // operands of the very first block product (everything after it is prefetched)
   {
-    const PairDesc d = ColPlan<M, MODE>(0).at(0, 0);
+    const PairDesc d = ColPlan<M>(0, MODE).at(0, 0);
     if (d.kind == PAIR_XY) { io.load_x(d.xi, xb); io.load_y(d.yi, yb); }
     else if (d.kind == PAIR_XX) { io.load_x(d.xi, xb); io.load_x(d.yi, yb); }
+    else if (d.kind == PAIR_XS) { io.load_x(d.xi, xb); io.load_s(d.yi, yb); }
   }
 
   for (int c = 0; c < 2 * M; ++c) {
-    const ColPlan<M, MODE> plan(c);
-    const bool defer_carry = (MODE == MONT_SQR) && plan.ncross > 0;
+    const ColPlan<M> plan(c, MODE);
+    const bool defer_carry = plan.ndouble > 0;
 
     // seed the accumulator with the carry-in, unless it must not be doubled
     if (!defer_carry) {
@@ -242,8 +258,8 @@ DKG_HD void mont_mul(const IO& io) {
     }
 
     for (int t = 0; t < plan.total; ++t) {
-      if (MODE == MONT_SQR && defer_carry && t == plan.ncross) {
-        // all cross products are in: double them, then add the carry-in
+      if ((MODE == MONT_SQR || MODE == MONT_MUL2S) && defer_carry && t == plan.ndouble) {
+        // all products that count twice are in: double them, then add the carry-in
         acc_merge<K>(a);
 #pragma unroll
         for (int p = 2 * K + 1; p > 0; p--) a.E[p] = (a.E[p] << 1) | (a.E[p - 1] >> 31);
@@ -269,11 +285,12 @@ DKG_HD void mont_mul(const IO& io) {
       nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
       if (t + 1 < plan.total) nx = plan.at(c, t + 1);
       else if (c + 1 < 2 * M) {
-        const ColPlan<M, MODE> np(c + 1);
+        const ColPlan<M> np(c + 1, MODE);
         if (np.total > 0) nx = np.at(c + 1, 0);
       }
       block_mac<K>(a, xb, yb, io, io.prefetch_desc(nx.kind, nx.yi));
-      if (nx.kind == PAIR_XY || nx.kind == PAIR_XX) io.load_x(nx.xi, xb);
+      if (nx.kind == PAIR_XY || nx.kind == PAIR_XX || nx.kind == PAIR_XS) io.load_x(nx.xi, xb);
+      else if (nx.kind == PAIR_SY2) io.load_s(nx.xi, xb);
       else if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
     }
     acc_merge<K>(a);

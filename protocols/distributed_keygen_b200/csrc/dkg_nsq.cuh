@@ -1,0 +1,197 @@
+// Exponentiation modulo N^2 with arithmetic modulo N only ("pair arithmetic").
+//
+// The modulus of threshold-Paillier partial decryption and of the encryption randomness is a
+// perfect square whose root N is public.  An element x of Z_{N^2} is held as a pair (a, b) of
+// L-limb integers (L = limbs of N plus >= 3 spare bits, R = 2^(32L)) with
+//        x * R  =  a + b * N * R^-1      (mod N^2),        0 <= a < 2N,  0 <= b < R.
+// Because (N R^-1)^2 = 0 (mod N^2):
+//   square  : a' = REDC(a^2)       with Montgomery quotient m  (a^2 = a' R - m N exactly)
+//             b' = REDC(2 a b) - m                             (mod N)
+//   multiply: a' = REDC(a c)       with quotient m
+//             b' = REDC(a d + b c) - m                         (mod N)
+// where REDC is Montgomery reduction modulo N.  A squaring costs one L-limb Montgomery squaring
+// and one L-limb Montgomery multiplication instead of one 2L-limb Montgomery squaring:
+// 15.9k instead of 26.7k wide multiply-accumulates at 2048-bit N (1.68x fewer), a multiplication
+// 21.5k instead of 33.9k.  Results are bit-identical to direct arithmetic modulo N^2 (the exit
+// step returns the canonical residue).  Derivation and bounds: DESIGN.md section 2.8; Python model:
+// tests/test_pair_model.py.
+//
+// "- m" is applied after the reduction as b'' + (R - m), then brought back into [0, R) with at
+// most one masked addition of (-R mod N) and one masked subtraction of N; b only matters mod N.
+#pragma once
+#include "dkg_modexp.cuh"
+#include "dkg_nsq_params_fwd.h"
+
+namespace dkg {
+
+
+// b <- b - m (mod N), kept in [0, R).  Bv: this lane's vector 0 of B in shared memory, mq: the
+// quotient blocks just written by the a-component's reduction (global, same vector layout),
+// N / Dneg: shared, CTA-uniform.  Whole vectors per access: conflict-free like the block loads.
+template <int K, int M>
+__device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const typename VecSel<K>::T* mq,
+                                           const uint32_t* Ns, const uint32_t* Dneg) {
+  using V = typename VecSel<K>::T;
+  constexpr int VW = VecSel<K>::VW;
+  constexpr int LV = K * M / VW;
+  // S = b + (R - m) = b + ~m + 1
+  uint32_t carry = 1;
+  for (int v = 0; v < LV; ++v) {
+    uint32_t bb[VW], mm[VW];
+    unpack(Bv[v * 32], bb);
+    unpack(mq[(size_t)v * 32], mm);
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      const uint64_t s = (uint64_t)bb[k] + (uint32_t)~mm[k] + carry;
+      bb[k] = (uint32_t)s;
+      carry = (uint32_t)(s >> 32);
+    }
+    V o; pack(o, bb); Bv[v * 32] = o;
+  }
+  // carry set: S >= R, dropping R leaves b - m >= 0.  Otherwise S = b - m + R: add (-R mod N),
+  // and if that passes R take N off once.
+  const uint32_t need = carry ^ 1u;
+  if (__any_sync(0xffffffffu, need)) {
+    const uint32_t mask = 0u - need;
+    uint32_t c2 = 0;
+    for (int v = 0; v < LV; ++v) {
+      uint32_t bb[VW];
+      unpack(Bv[v * 32], bb);
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        const uint64_t s = (uint64_t)bb[k] + (Dneg[v * VW + k] & mask) + c2;
+        bb[k] = (uint32_t)s;
+        c2 = (uint32_t)(s >> 32);
+      }
+      V o; pack(o, bb); Bv[v * 32] = o;
+    }
+    if (__any_sync(0xffffffffu, c2)) {
+      const uint32_t mask2 = 0u - c2;
+      uint32_t borrow = 0;
+      for (int v = 0; v < LV; ++v) {
+        uint32_t bb[VW];
+        unpack(Bv[v * 32], bb);
+#pragma unroll
+        for (int k = 0; k < VW; ++k) {
+          const uint64_t d = (uint64_t)bb[k] - (Ns[v * VW + k] & mask2) - borrow;
+          bb[k] = (uint32_t)d;
+          borrow = (uint32_t)(d >> 63);
+        }
+        V o; pack(o, bb); Bv[v * 32] = o;
+      }
+    }
+  }
+}
+
+template <int K, int M>
+__global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const NsqParams p) {
+  using V = typename VecSel<K>::T;
+  constexpr int VW = VecSel<K>::VW;
+  constexpr int Lp = K * M;
+  constexpr int LV = Lp / VW;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // N[Lp] | NINV[K] | DNEG[Lp]
+  constexpr int UNI = ((2 * Lp + K) * 4 + 15) / 16 * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * Lp + K; i += blockDim.x) U32[i] = p.consts[i];
+  __syncthreads();
+  const uint32_t* Ns32 = U32;
+  const uint32_t* Dneg = U32 + Lp + K;
+
+  V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * 2 * LV * 32;
+  V* Bw = Aw + LV * 32;
+  uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
+  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
+  const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
+  const V* R2A = Cg, *R2B = Cg + LV, *ONEA = Cg + 2 * LV, *ONEB = Cg + 3 * LV, *PLAIN1 = Cg + 4 * LV, *ZERO = Cg + 5 * LV;
+
+  const unsigned gwarp = blockIdx.x * nwarps + warp;
+  uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
+  V* tab = reinterpret_cast<V*>(scratch32);   // entry d (1-based): a at ((d-1)*2)*LV*32, b right after
+  V* Qg = reinterpret_cast<V*>(scratch32 + p.scratch_q_offset);
+
+  const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(Aw + lane);
+  const uint32_t b_s = (uint32_t)__cvta_generic_to_shared(Bw + lane);
+  WarpIO<K, M> io;
+  io.ns = (uint32_t)__cvta_generic_to_shared(Ns32);
+  io.nis = (uint32_t)__cvta_generic_to_shared(Ns32 + Lp);
+  io.Qg = Qg + lane;
+
+  // (A, B) <- (A, B) * (c, d): c, d in global memory with vector stride `st`
+  auto pair_mul = [&](const V* c, const V* d, int st) {
+    io.xs = b_s; io.ss = a_s; io.Y = c; io.ystride = st; io.Y2 = d; io.y2stride = st;
+    mont_call<K, M, MONT_MULADD>(io);                 // B <- REDC(B c + A d)
+    io.xs = a_s;
+    mont_call<K, M, MONT_MUL>(io);                    // A <- REDC(A c), quotient m in Q
+    pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
+  };
+  auto pair_sqr = [&]() {
+    io.xs = b_s; io.ss = a_s;
+    mont_call<K, M, MONT_MUL2S>(io);                  // B <- REDC(2 B A)
+    io.xs = a_s;
+    mont_call<K, M, MONT_SQR>(io);                    // A <- REDC(A^2), quotient m in Q
+    pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
+  };
+
+  const unsigned long long ngroups = (p.count + 31ull) / 32ull;
+  for (;;) {
+    unsigned int g = 0;
+    if (lane == 0) g = atomicAdd(p.counter, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups) break;
+    const unsigned long long first = (unsigned long long)g * 32ull;
+    const int cnt = (int)((p.count - first) < 32ull ? (p.count - first) : 32ull);
+
+    // rows of 2*Lp limbs: a then b; idle lanes get the pair of 1
+    for (int r = 0; r < 32; ++r) {
+      const uint32_t* row = p.pairs_in + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
+      for (int l = lane; l < Lp; l += 32) {
+        const int i = ((l / VW) * 32 + r) * VW + (l % VW);
+        Aw32[i] = (r < cnt) ? row[l] : (l == 0 ? 1u : 0u);
+        Bw32[i] = (r < cnt) ? row[Lp + l] : 0u;
+      }
+    }
+    __syncwarp();
+
+    pair_mul(R2A, R2B, 1);   // into the Montgomery domain: value c * R
+    if (p.ndigits == 0) {
+      for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = ONEA[v]; Bw[v * 32 + lane] = ONEB[v]; }
+    } else {
+      const int tsize = (1 << p.wbits) - 1;
+      auto tab_a = [&](int d) -> V* { return tab + (size_t)(d - 1) * 2 * LV * 32 + lane; };
+      auto tab_b = [&](int d) -> V* { return tab + ((size_t)(d - 1) * 2 + 1) * LV * 32 + lane; };
+      for (int v = 0; v < LV; ++v) { tab_a(1)[(size_t)v * 32] = Aw[v * 32 + lane]; tab_b(1)[(size_t)v * 32] = Bw[v * 32 + lane]; }
+      for (int d = 2; d <= tsize; ++d) {
+        pair_mul(tab_a(1), tab_b(1), 32);
+        V* da = tab_a(d); V* db = tab_b(d);
+        for (int v = 0; v < LV; ++v) { da[(size_t)v * 32] = Aw[v * 32 + lane]; db[(size_t)v * 32] = Bw[v * 32 + lane]; }
+      }
+      {
+        const int d0 = p.digits[0];
+        const V* sa = tab_a(d0); const V* sb = tab_b(d0);
+        for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = sa[(size_t)v * 32]; Bw[v * 32 + lane] = sb[(size_t)v * 32]; }
+      }
+      for (int t = 1; t < p.ndigits; ++t) {
+        for (int s = 0; s < p.wbits; ++s) pair_sqr();
+        const int d = p.digits[t];
+        if (d == 0) pair_mul(ONEA, ONEB, 1);
+        else pair_mul(tab_a(d), tab_b(d), 32);
+      }
+    }
+    pair_mul(PLAIN1, ZERO, 1);   // out of the Montgomery domain: the pair now stands for the result itself
+    __syncwarp();
+
+    for (int r = 0; r < cnt; ++r) {
+      uint32_t* row = p.pairs_out + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
+      for (int l = lane; l < Lp; l += 32) {
+        const int i = ((l / VW) * 32 + r) * VW + (l % VW);
+        row[l] = Aw32[i];
+        row[Lp + l] = Bw32[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace dkg

@@ -18,9 +18,13 @@ class ModexpContext:
     exponent: the batched form of ``pow_mod`` (+ ``mod_inv`` for negative exponents) at
     ``paillier_shared_key.py:89-92`` of the reference."""
 
-    def __init__(self, modulus: int, exponent: int, device: int = 0) -> None:
+    def __init__(self, modulus: int, exponent: int, device: int = 0, root: int | None = None) -> None:
+        """``root``: if given, ``modulus`` must equal ``root ** 2``; the exponentiation then runs in
+        pair arithmetic modulo ``root`` (same results, ~1.6x fewer multiplications)."""
         if modulus <= 0 or modulus % 2 == 0:
             raise ValueError("modulus must be a positive odd integer")
+        if root is not None and root * root != modulus:
+            raise ValueError("root ** 2 must equal the modulus")
         self.modulus = modulus
         self.exponent = exponent
         self.device = device
@@ -30,12 +34,23 @@ class ModexpContext:
         self._mod = int_to_limbs(modulus, self.limbs)
         self._exp = int_to_limbs(mag, exp_limbs)
         handle = ctypes.c_void_p()
-        _native.check(
-            _native.lib.dkg_modexp_ctx_create(
-                device, self._mod.ctypes.data, self.limbs, self._exp.ctypes.data, exp_limbs,
-                1 if exponent < 0 else 0, ctypes.byref(handle),
+        if root is None:
+            _native.check(
+                _native.lib.dkg_modexp_ctx_create(
+                    device, self._mod.ctypes.data, self.limbs, self._exp.ctypes.data, exp_limbs,
+                    1 if exponent < 0 else 0, ctypes.byref(handle),
+                )
             )
-        )
+        else:
+            root_limbs = limbs_for_bits(root.bit_length())
+            self._root = int_to_limbs(root, root_limbs)
+            _native.check(
+                _native.lib.dkg_modexp_ctx_create_nsq(
+                    device, self._root.ctypes.data, root_limbs, self._exp.ctypes.data, exp_limbs,
+                    1 if exponent < 0 else 0, ctypes.byref(handle),
+                )
+            )
+        self.root = root
         self._h = handle
 
     def close(self) -> None:
@@ -50,10 +65,14 @@ class ModexpContext:
             pass
 
     def info(self) -> dict[str, int]:
-        arr = (ctypes.c_int * 8)()
+        arr = (ctypes.c_int * 12)()
         _native.check(_native.lib.dkg_modexp_ctx_info(self._h, ctypes.byref(arr)))
-        keys = ["K", "M", "padded_limbs", "window_bits", "windows", "exponent_bits", "warps_per_cta", "ctas"]
-        return dict(zip(keys, list(arr)))
+        keys = ["K", "M", "padded_limbs", "window_bits", "windows", "exponent_bits", "warps_per_cta", "ctas",
+                "pair_arithmetic", "pair_K", "pair_M", "pair_warps_per_cta"]
+        out = dict(zip(keys, list(arr)))
+        if out["pair_arithmetic"]:
+            out["warps_per_cta"] = out["pair_warps_per_cta"]
+        return out
 
     def modexp_limbs(self, bases: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
         """bases: uint32 [count, limbs] (values < modulus).  Returns (out [count, limbs], status)."""
@@ -148,7 +167,7 @@ class EncryptContext:
         self.n = n
         self.n_limbs = limbs_for_bits(n.bit_length())
         self._n = int_to_limbs(n, self.n_limbs)
-        self._ctx = ModexpContext(n * n, n, device)
+        self._ctx = ModexpContext(n * n, n, device)  # (1 + mN) epilogue runs in the direct kernel
         self.n2_limbs = self._ctx.limbs
 
     def close(self) -> None:

@@ -83,7 +83,7 @@ class PaillierSharedKey:
 
     def _modexp_ctx(self) -> ModexpContext:
         if self._modexp is None:
-            self._modexp = ModexpContext(self.n_square, self.partial_decrypt_exponent(), self.device)
+            self._modexp = ModexpContext(self.n_square, self.partial_decrypt_exponent(), self.device, root=self.n)
         return self._modexp
 
     def _combine_ctx(self) -> CombineContext:

@@ -9,6 +9,8 @@ namespace {
 template <int K, int M>
 struct HostIO {
   uint32_t* X; const uint32_t* Y; uint32_t* Q; const uint32_t* N; const uint32_t* NI;
+  const uint32_t* S = nullptr; const uint32_t* Y2 = nullptr;
+  void load_s(int i, uint32_t (&r)[K]) const { std::memcpy(r, S + i * K, K * 4); }
   void load_x(int i, uint32_t (&r)[K]) const { std::memcpy(r, X + i * K, K * 4); }
   void load_y(int j, uint32_t (&r)[K]) const { std::memcpy(r, Y + j * K, K * 4); }
   void load_q(int i, uint32_t (&r)[K]) const { std::memcpy(r, Q + i * K, K * 4); }
@@ -20,6 +22,8 @@ struct HostIO {
     if (kind == dkg::PAIR_XY) return Prefetch{Y + blk * K};
     if (kind == dkg::PAIR_XX) return Prefetch{X + blk * K};
     if (kind == dkg::PAIR_NQ) return Prefetch{Q + blk * K};
+    if (kind == dkg::PAIR_XS) return Prefetch{S + blk * K};
+    if (kind == dkg::PAIR_SY2) return Prefetch{Y2 + blk * K};
     return Prefetch{nullptr};
   }
   void prefetch_load(const Prefetch& pf, int v, uint32_t (&r)[K]) const {
@@ -30,26 +34,35 @@ struct HostIO {
 };
 
 template <int K, int M>
-int run(int mode, uint32_t* x, const uint32_t* y, const uint32_t* n, const uint32_t* ninv, int canon) {
+int run(int mode, uint32_t* x, const uint32_t* y, const uint32_t* n, const uint32_t* ninv, int canon,
+        const uint32_t* s_op, const uint32_t* y2) {
   uint32_t q[K * M];
   std::memset(q, 0, sizeof(q));
   HostIO<K, M> io{x, y, q, n, ninv};
-  if (mode == 0) dkg::mont_mul<K, M, dkg::MONT_MUL>(io);
-  else if (mode == 1) { io.Y = x; dkg::mont_mul<K, M, dkg::MONT_MUL>(io); }
-  else if (mode == 3) dkg::mont_mul<K, M, dkg::MONT_SQR>(io);
-  else dkg::mont_mul<K, M, dkg::MONT_REDC>(io);
+  if (mode == 0) dkg::mont_mul<K, M>(io, dkg::MONT_MUL);
+  else if (mode == 1) { io.Y = x; dkg::mont_mul<K, M>(io, dkg::MONT_MUL); }
+  else if (mode == 3) dkg::mont_mul<K, M>(io, dkg::MONT_SQR);
+  else if (mode == 4) { io.S = y; dkg::mont_mul<K, M>(io, dkg::MONT_MUL2S); }                 // x <- 2*x*y/R
+  else if (mode == 5) { io.S = s_op; io.Y2 = y2; dkg::mont_mul<K, M>(io, dkg::MONT_MULADD); }  // x <- (x*y + s*y2)/R
+  else dkg::mont_mul<K, M>(io, dkg::MONT_REDC);
   if (canon) dkg::canonicalize<K, M>(io, canon);
   return 0;
 }
 }  // namespace
 
-#define CASE(K_, M_) if (K == K_ && M == M_) return run<K_, M_>(mode, x, y, n, ninv, canon);
+#define CASE(K_, M_) if (K == K_ && M == M_) return run<K_, M_>(mode, x, y, n, ninv, canon, s_op, y2);
 
 // mode 0: x <- x*y/R mod n; 1: x <- x*x/R (y aliased to x, in place); 2: x <- x/R;
-// 3: x <- x*x/R through the dedicated squaring path.
+// 3: x <- x*x/R through the dedicated squaring path; 4: x <- 2*x*y/R (y as the second shared
+// operand); 5: x <- (x*y + s*y2)/R.
+extern "C" int host_mont2(int K, int M, int mode, uint32_t* x, const uint32_t* y, const uint32_t* n,
+                          const uint32_t* ninv, int canon, const uint32_t* s_op, const uint32_t* y2) {
+  CASE(4, 1) CASE(4, 3) CASE(4, 2) CASE(4, 5) CASE(6, 3) CASE(8, 4) CASE(12, 3) CASE(16, 2)
+  CASE(16, 8) CASE(12, 11) CASE(22, 3) CASE(22, 6) CASE(16, 16) CASE(14, 5) CASE(12, 6)
+  return -1;
+}
+
 extern "C" int host_mont(int K, int M, int mode, uint32_t* x, const uint32_t* y, const uint32_t* n,
                          const uint32_t* ninv, int canon) {
-  CASE(4, 1) CASE(4, 3) CASE(4, 2) CASE(4, 5) CASE(6, 3) CASE(8, 4) CASE(12, 3) CASE(16, 2)
-  CASE(16, 8) CASE(12, 11) CASE(22, 3) CASE(22, 6) CASE(16, 16)
-  return -1;
+  return host_mont2(K, M, mode, x, y, n, ninv, canon, nullptr, nullptr);
 }

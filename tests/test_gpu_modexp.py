@@ -87,6 +87,45 @@ def test_negative_exponent_large_batch_with_non_units(eng):
     ctx.close()
 
 
+def test_square_modulus_pair_arithmetic_matches_direct_kernel(eng):
+    """Contexts created with the root N (pair arithmetic modulo N, csrc/dkg_nsq.cuh) against
+    contexts on N^2 itself and against pow(): all widths, signed exponents, non-units."""
+    import math
+
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+
+    rng = random.Random(404)
+    for bits in [9, 20, 61, 67, 130, 257, 515, 1030, 2048, 2051]:
+        p = rng.getrandbits(bits // 2) | 1 | (1 << (bits // 2 - 1))
+        q = rng.getrandbits(bits - bits // 2) | 1 | (1 << (bits - bits // 2 - 1))
+        n, n2 = p * q, (p * q) ** 2
+        for e in [0, 1, 3, rng.getrandbits(bits + 40), -rng.getrandbits(bits + 40)]:
+            fast = eng.ModexpContext(n2, e, root=n)
+            assert fast.info()["pair_arithmetic"] == 1
+            bases = [0, 1, n2 - 1, n, n + 1, n - 1] + [rng.randrange(n2) for _ in range(70)]
+            if e < 0:
+                bases = [b for b in bases if math.gcd(b, n) == 1]
+            assert fast.modexp(bases) == [pow(b, e, n2) for b in bases], (bits, e)
+            fast.close()
+    # non-units under a negative exponent: exact per-element status through the fallback
+    p, q = (1 << 61) - 1, (1 << 31) - 1
+    n, n2 = p * q, (p * q) ** 2
+    e = -rng.getrandbits(150)
+    fast = eng.ModexpContext(n2, e, root=n)
+    bases = [rng.randrange(1, n2) for _ in range(500)]
+    bases[3], bases[77], bases[499] = p, 0, q * q
+    out, status = fast.modexp_limbs(ints_to_limbs(bases, fast.limbs))
+    vals = limbs_to_ints(out)
+    for i, b in enumerate(bases):
+        if math.gcd(b, n) != 1:
+            assert status[i] == 1 and vals[i] == 0
+        else:
+            assert status[i] == 0 and vals[i] == pow(b, e, n2)
+    fast.close()
+    with pytest.raises(ValueError):
+        eng.ModexpContext(n2, 5, root=n + 2)
+
+
 def test_partial_decrypt_golden_fixture_keys(eng, fixture_vectors):
     """The reference's 24 golden keys: c^(e_i) mod N^2 must equal what the reference's
     PaillierSharedKey.partial_decrypt returned (tests/golden/fixture_vectors.json)."""

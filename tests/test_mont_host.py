@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "protocols", "distributed_keygen_b200", "csrc")
 
 SHAPES = [(4, 1), (4, 3), (4, 2), (4, 5), (6, 3), (8, 4), (12, 3), (16, 2), (16, 8), (12, 11),
-          (22, 3), (22, 6), (16, 16)]
+          (22, 3), (22, 6), (16, 16), (14, 5), (12, 6)]
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +26,11 @@ def lib(tmp_path_factory):
          os.path.join(ROOT, "tests", "host", "mont_host.cpp")],
         check=True,
     )
-    return ctypes.CDLL(str(out))
+    lib = ctypes.CDLL(str(out))
+    vp = ctypes.c_void_p
+    lib.host_mont.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+    lib.host_mont2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp]
+    return lib
 
 
 def _limbs(v: int, n: int) -> np.ndarray:
@@ -91,3 +95,32 @@ def test_mont_exponentiation_chain_host(lib):
         if bit == "1":
             acc = _call(lib, K, M, 0, acc, b_m, n, ninv, 0)
     assert _call(lib, K, M, 2, acc, 0, n, ninv, 1) == pow(base, e, n)
+
+
+@pytest.mark.parametrize("K,M", [(4, 2), (12, 6), (14, 5), (16, 4) if False else (16, 2), (22, 3)])
+def test_pair_modes_host(lib, K, M):
+    """MONT_MUL2S (x <- 2xy/R) and MONT_MULADD (x <- (xy + s y2)/R) used by the mod N^2 pair
+    arithmetic, with operands up to R and a modulus with >= 3 spare bits."""
+    rng = random.Random(7000 + 10 * K + M)
+    L = K * M
+    R = 1 << (32 * L)
+    W = 1 << (32 * K)
+    for trial in range(12):
+        n = rng.getrandbits(32 * L - 3) | 1 | (1 << (32 * L - 4))
+        ninv = (-pow(n, -1, W)) % W
+        r_inv = pow(R, -1, n)
+        x, y = rng.randrange(R), rng.randrange(2 * n)
+        s_op, y2 = rng.randrange(2 * n), rng.randrange(R)
+        if trial == 0:
+            x, y = R - 1, 2 * n - 1
+        xa, ya, na, ia = _limbs(x, L), _limbs(y, L), _limbs(n, L), _limbs(ninv, K)
+        sa, y2a = _limbs(s_op, L), _limbs(y2, L)
+        assert lib.host_mont2(K, M, 4, xa.ctypes.data, ya.ctypes.data, na.ctypes.data, ia.ctypes.data, 0,
+                              sa.ctypes.data, y2a.ctypes.data) == 0
+        got = _val(xa)
+        assert got < R and got % n == (2 * x * y * r_inv) % n, (K, M, trial, "mul2s")
+        xa = _limbs(x, L)
+        assert lib.host_mont2(K, M, 5, xa.ctypes.data, ya.ctypes.data, na.ctypes.data, ia.ctypes.data, 0,
+                              sa.ctypes.data, y2a.ctypes.data) == 0
+        got = _val(xa)
+        assert got < R and got % n == ((x * y + s_op * y2) * r_inv) % n, (K, M, trial, "muladd")
