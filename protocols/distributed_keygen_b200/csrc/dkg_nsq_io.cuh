@@ -73,13 +73,20 @@ __global__ void __launch_bounds__(64) nsq_exit_kernel(const NsqIoParams p) {
   const uint32_t* pr = p.in + idx * (unsigned long long)(2 * Lp);
   uint32_t a[kNsqMaxL], h[kNsqMaxL], t[kNsqMaxL + 2], one[kNsqMaxL];
   for (int l = 0; l < Lp; ++l) { a[l] = pr[l]; h[l] = pr[Lp + l]; one[l] = (l == 0) ? 1u : 0u; }
-  // a < 2N: canonical a
+  gen_mont_mul(h, one, 1, N, p.n0inv, Lp, t);                  // h = b R^-1 mod N, canonical
+  // a < 2N as an integer: a = a' + N moves one N into h (h <- h + 1 mod N)
   {
     uint32_t borrow = 0;
     for (int l = 0; l < Lp; ++l) { const uint64_t d = (uint64_t)a[l] - N[l] - borrow; t[l] = (uint32_t)d; borrow = (uint32_t)(d >> 63); }
-    if (borrow == 0) for (int l = 0; l < Lp; ++l) a[l] = t[l];
+    if (borrow == 0) {
+      for (int l = 0; l < Lp; ++l) a[l] = t[l];
+      uint64_t carry = 1;
+      for (int l = 0; l < Lp; ++l) { const uint64_t s2 = (uint64_t)h[l] + carry; h[l] = (uint32_t)s2; carry = s2 >> 32; }
+      uint32_t diff = 0;
+      for (int l = 0; l < Lp; ++l) diff |= h[l] ^ N[l];
+      if (diff == 0) for (int l = 0; l < Lp; ++l) h[l] = 0;
+    }
   }
-  gen_mont_mul(h, one, 1, N, p.n0inv, Lp, t);                  // h = b R^-1 mod N, canonical
   // y = a + N * h  (< N^2), low io_limbs limbs
   uint32_t* o = p.out + idx * (unsigned long long)p.io_limbs;
   uint32_t c0 = 0, c1 = 0, c2 = 0;

@@ -59,7 +59,17 @@ def modexp_pair(c, e, N, R):
             acc = pair_mul(*acc, *x, N, R, Ninv)
     a, b = pair_mul(*acc, *p1, N, R, Ninv)
     h, _ = redc_q(b, N, R, Ninv)
-    return (a % N + (h % N) * N) % N2
+    return (a + (h % N) * N) % N2  # a is an integer < 2N: it must not be reduced without moving N into h
+
+
+def test_pair_arithmetic_nilpotent_and_non_unit_bases():
+    """Composite-radical cases (a component reaching N exactly) that once exposed a missing carry
+    from a into h in the exit step."""
+    N = 9 * 29
+    R = 1 << 128
+    for c in (41934, 87, 174 * 5, N * 7, 3 * 29 * 11):
+        for e in (1, 2, 3, 4, 7, 64, 501409110107081):
+            assert modexp_pair(c, e, N, R) == pow(c, e, N * N)
 
 
 def test_pair_arithmetic_equals_pow():
