@@ -224,7 +224,7 @@ int choose_window(int ebits) {
 }
 
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
-                      size_t count, cudaStream_t stream, bool* handled);
+                      size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows = nullptr, int m_limbs = 0);
 
 int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
                   const uint32_t* d_final_mul, size_t count, cudaStream_t stream) {
@@ -277,7 +277,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
 // Falls back to the direct kernel (handled = false) when a chain of the batched inversion hit a
 // non-unit, so that the per-element status comes out exact.
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
-                      size_t count, cudaStream_t stream, bool* handled) {
+                      size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs) {
   DeviceState* d = ctx->dev;
   *handled = false;
   const unsigned long long ngroups = (count + 31) / 32;
@@ -323,6 +323,7 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   if (rc != DKG_OK) return rc;
   dkg::NsqIoParams e{};
   e.in = src; e.out = pairs; e.count = count; e.io_limbs = ctx->limbs; e.Lp = Lp; e.consts = ctx->d_nio; e.n0inv = ctx->n_n0inv;
+  e.mrows = nullptr; e.m_limbs = 0;
   dkg::nsq_entry_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(e);
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::NsqParams q{};
@@ -331,7 +332,7 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   q.scratch_q_offset = ctx->nscratch_q_offset; q.counter = d->counter;
   ctx->nsq_kernel<<<ctas, ctx->nwarps * 32, ctx->nsmem, stream>>>(q);
   dkg::NsqIoParams x = e;
-  x.in = pairs; x.out = d_out;
+  x.in = pairs; x.out = d_out; x.mrows = d_mrows; x.m_limbs = m_limbs;
   dkg::nsq_exit_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(x);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(3);
@@ -766,7 +767,11 @@ extern "C" int dkg_encrypt_batch(dkg_modexp_ctx* ctx, const uint32_t* n, int n_l
     g_launches.fetch_add(1);
   }
   CUDA_TRY(cudaGetLastError());
-  int rc = launch_modexp(ctx, d_base, d_out, nullptr, m ? d_fm : nullptr, count, d->stream);
+  int rc = DKG_OK;
+  bool handled = false;
+  if (ctx->nsq && !getenv("DKG_NO_NSQ"))  // r^N in pair arithmetic, (1 + m N) folded into the exit step
+    rc = launch_modexp_nsq(ctx, d_base, d_out, nullptr, count, d->stream, &handled, m ? d_m : nullptr, n_limbs);
+  if (rc == DKG_OK && !handled) rc = launch_modexp(ctx, d_base, d_out, nullptr, m ? d_fm : nullptr, count, d->stream);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream));
   CUDA_TRY(cudaStreamSynchronize(d->stream));

@@ -21,6 +21,10 @@ struct NsqIoParams {
   // device constants: N[Lp] | R2N[Lp] (R^2 mod N) | NINVPOS[Lp] (N^-1 mod R)
   const uint32_t* consts;
   uint32_t n0inv;           // -N^-1 mod 2^32
+  // exit only, optional: plaintexts m (< N), [count][m_limbs]: the result is multiplied by (1 + m N)
+  // (Paillier encryption with g = N + 1): y0 + N (y1 + y0 m mod N)
+  const uint32_t* mrows;
+  int m_limbs;
 };
 
 __global__ void __launch_bounds__(64) nsq_entry_kernel(const NsqIoParams p) {
@@ -86,6 +90,20 @@ __global__ void __launch_bounds__(64) nsq_exit_kernel(const NsqIoParams p) {
       for (int l = 0; l < Lp; ++l) diff |= h[l] ^ N[l];
       if (diff == 0) for (int l = 0; l < Lp; ++l) h[l] = 0;
     }
+  }
+  if (p.mrows != nullptr) {
+    // (a + N h)(1 + m N) = a + N (h + a m)  (mod N^2)
+    const uint32_t* R2N = N + Lp;
+    const uint32_t* mr = p.mrows + idx * (unsigned long long)p.m_limbs;
+    uint32_t am[kNsqMaxL], mm[kNsqMaxL];
+    for (int l = 0; l < Lp; ++l) { am[l] = a[l]; mm[l] = l < p.m_limbs ? mr[l] : 0u; }
+    gen_mont_mul(am, mm, 1, N, p.n0inv, Lp, t);      // a m R^-1
+    gen_mont_mul(am, R2N, 1, N, p.n0inv, Lp, t);     // a m mod N
+    uint64_t carry = 0;
+    for (int l = 0; l < Lp; ++l) { const uint64_t s2 = (uint64_t)h[l] + am[l] + carry; h[l] = (uint32_t)s2; carry = s2 >> 32; }
+    uint32_t borrow = 0;
+    for (int l = 0; l < Lp; ++l) { const uint64_t d = (uint64_t)h[l] - N[l] - borrow; t[l] = (uint32_t)d; borrow = (uint32_t)(d >> 63); }
+    if (borrow == 0) for (int l = 0; l < Lp; ++l) h[l] = t[l];
   }
   // y = a + N * h  (< N^2), low io_limbs limbs
   uint32_t* o = p.out + idx * (unsigned long long)p.io_limbs;

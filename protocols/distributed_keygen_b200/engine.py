@@ -167,7 +167,7 @@ class EncryptContext:
         self.n = n
         self.n_limbs = limbs_for_bits(n.bit_length())
         self._n = int_to_limbs(n, self.n_limbs)
-        self._ctx = ModexpContext(n * n, n, device)  # (1 + mN) epilogue runs in the direct kernel
+        self._ctx = ModexpContext(n * n, n, device, root=n)
         self.n2_limbs = self._ctx.limbs
 
     def close(self) -> None:
