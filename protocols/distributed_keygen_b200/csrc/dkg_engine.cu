@@ -800,8 +800,13 @@ struct GroupedPlan {
 };
 
 int plan_grouped(DeviceState* d, int limbs, int ebits, size_t count, GroupedPlan* plan) {
-  for (const Shape& sh : kShapes)
-    if (sh.K * sh.M >= limbs && (plan->kernel = lookup_grouped(sh.K, sh.M)) != nullptr) { plan->shape = sh; break; }
+  if (const char* f = getenv("DKG_GROUPED_SHAPE")) {  // tuning knob: "K,M"
+    int k = 0, m = 0;
+    if (sscanf(f, "%d,%d", &k, &m) == 2 && k * m >= limbs && (plan->kernel = lookup_grouped(k, m)) != nullptr) plan->shape = Shape{k, m};
+  }
+  if (!plan->kernel)
+    for (const Shape& sh : kShapes)
+      if (sh.K * sh.M >= limbs && (plan->kernel = lookup_grouped(sh.K, sh.M)) != nullptr) { plan->shape = sh; break; }
   if (!plan->kernel) return fail(DKG_ERR_UNSUPPORTED, "modulus wider than the grouped kernel shapes (132 limbs)");
   plan->Lp = plan->shape.K * plan->shape.M;
   plan->K = plan->shape.K;

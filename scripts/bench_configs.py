@@ -38,8 +38,8 @@ def rand_rows(count, limbs, top_bits, seed):
     return arr
 
 
-def time_modexp(name, modulus, exponent, waves=2, check=True):
-    ctx = eng.ModexpContext(modulus, exponent)
+def time_modexp(name, modulus, exponent, waves=2, check=True, root=None):
+    ctx = eng.ModexpContext(modulus, exponent, root=root)
     info = ctx.info()
     B = waves * info["ctas"] * info["warps_per_cta"] * 32
     L = ctx.limbs
@@ -67,7 +67,7 @@ def time_modexp(name, modulus, exponent, waves=2, check=True):
     line = {
         "config": name, "op": "modexp", "count": B, "ms": ms, "per_s": B / ms * 1e3,
         "modulus_bits": modulus.bit_length(), "exponent_bits": ebits * (1 if exponent >= 0 else -1),
-        "kernel_shape": info, "canonical_Tmac_per_s": B * canonical_macs(ebits, L) / ms / 1e9, "ok": ok,
+        "pair_arithmetic": bool(info.get("pair_arithmetic")), "kernel_shape": info, "canonical_Tmac_per_s": B * canonical_macs(ebits, L) / ms / 1e9, "ok": ok,
     }
     print(json.dumps(line), flush=True)
     ctx.close()
@@ -86,7 +86,7 @@ def main():
         dk = okeys.dealer_key_from_json(dv[name]["key"])
         for pid in sorted(dk.keys)[: (2 if args.quick else 2 * dk.t + 1)]:
             k = dk.keys[pid]
-            time_modexp(f"{name}/party{pid}", k.n_square, k.partial_decrypt_exponent(), waves=1)
+            time_modexp(f"{name}/party{pid}", k.n_square, k.partial_decrypt_exponent(), waves=1, root=k.n)
     # cfg3 combine-only rate (5 partials)
     dk = okeys.dealer_key_from_json(dv["cfg3_k2048_p5_t2_exact"]["key"])
     key = dk.keys[1]
@@ -108,10 +108,11 @@ def main():
     # cfg4: key_length 4096
     dk = okeys.dealer_key_from_json(dv["cfg4_k4096_p3_t1_exact"]["key"])
     k = dk.keys[1]
-    time_modexp("cfg4_k4096/partial_decrypt", k.n_square, k.partial_decrypt_exponent(), waves=1)
-    time_modexp("cfg4_k4096/r^N", k.n_square, dk.n, waves=1)
+    time_modexp("cfg4_k4096/partial_decrypt", k.n_square, k.partial_decrypt_exponent(), waves=1, root=k.n)
+    time_modexp("cfg4_k4096/partial_decrypt (direct kernel)", k.n_square, k.partial_decrypt_exponent(), waves=1)
+    time_modexp("cfg4_k4096/r^N", k.n_square, dk.n, waves=1, root=dk.n)
     dk2 = okeys.dealer_key_from_json(dv["cfg2_k2048_p3_t1_exact"]["key"])
-    time_modexp("cfg2_k2048/r^N", dk2.n * dk2.n, dk2.n, waves=1)
+    time_modexp("cfg2_k2048/r^N", dk2.n * dk2.n, dk2.n, waves=1, root=dk2.n)
 
     # cfg5: biprimality batch sweep (party 1 exponents ~2046 bits, 40 bases per candidate)
     rng = random.Random(5)
