@@ -140,7 +140,7 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(dk, cores: int, sample: int, seed: int) -> dict:
+def cpu_baseline(dk, cores: int, sample: int, seed: int, cpython: bool = True) -> dict:
     """GMP mpz_powm (+ mpz_invert for the negative exponent) on `cores` pthreads over `sample`
     ciphertexts for each of the d+1 parties, plus the combination in CPython ints: the
     reference's CPU path with the [gmpy] extra (gmpy2.powmod wraps mpz_powm)."""
@@ -161,10 +161,24 @@ def cpu_baseline(dk, cores: int, sample: int, seed: int) -> dict:
     for i in range(sample):
         key1.decrypt({pid: partial_rows[pid][i] for pid in partial_rows})
     secs = time.perf_counter() - t0
-    return {
-        "value": sample / secs, "unit": UNIT, "cores": cores, "kind": "port",
+    # secondary line: CPython pow on one core (the reference without its [gmpy] extra)
+    out = {
+        "value": sample / secs, "unit": UNIT, "cores": cores, "kind": "port", "secs": secs,
         "sample": f"{sample} ciphertexts x 3 parties GMP 6.3 mpz_powm/mpz_invert via oracle/c/gmp_batch.c on {cores} pthreads + CPython combine, {secs:.1f} s",
     }
+    if cpython:
+        k = min(4, sample)
+        ints = gmp.limbs_to_ints(cts[:k])
+        t1 = time.perf_counter()
+        for pid in partial_rows:
+            e = dk.keys[pid].partial_decrypt_exponent()
+            for c in ints:
+                got = pow(pow(c, -1, n2), -e, n2) if e < 0 else pow(c, e, n2)
+            assert got == partial_rows[pid][k - 1], "GMP and CPython disagree"
+        py_secs = time.perf_counter() - t1
+        out["cpython_pow_1core"] = {"value": k / py_secs, "unit": UNIT,
+                                    "sample": f"{k} ciphertexts x 3 parties, builtin pow"}
+    return out
 
 
 def run_reference(args) -> None:
@@ -175,12 +189,11 @@ def run_reference(args) -> None:
     cores = os.cpu_count() or 1
     sample = args.ref_sample or max(cores * 96, 256)
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(dk, cores, max(cores, 16), 1)
-    t0 = time.perf_counter()
+        cpu_baseline(dk, cores, max(cores, 16), 1, cpython=False)
     vals = []
     for s in range(args.steps):
-        vals.append(cpu_baseline(dk, cores, sample, 100 + s))
-    secs = time.perf_counter() - t0
+        vals.append(cpu_baseline(dk, cores, sample, 100 + s, cpython=False))
+    secs = sum(v["secs"] for v in vals)
     value = sample * args.steps / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,

@@ -147,6 +147,20 @@ int dkg_small_prime_sieve(int device, const uint32_t* moduli, const uint32_t* pr
 int dkg_biprime_verdict(int device, const uint32_t* moduli, const uint32_t* v, int parties, int correct,
                         uint8_t* ok, size_t groups, int limbs);
 
+/* ---- wire format of the batched partial-decryption message (host only, no device work) ------- */
+/* The reference broadcasts {"content": "partial_decryption_sequence", "value": [int, ...]}
+ * (distributed_keygen.py:476-484) and reads it back at :497-505.  These two convert between limb
+ * rows and the msgpack array that is the "value": integers >= 2^64 as the reference's serializer
+ * tags them, {"type": "int", "data": little-endian two's complement of (bits+8)/8 bytes}, smaller
+ * ones as minimal native msgpack integers.
+ * encode: out == NULL queries the size; *written = bytes needed / written.
+ * decode: rows == NULL queries the element count; *consumed = bytes of buf the array occupied;
+ * DKG_ERR_INVALID for a negative value, one wider than `limbs`, or malformed input. */
+int dkg_wire_encode_rows(const uint32_t* rows, size_t count, int limbs, uint8_t* out,
+                         size_t capacity, size_t* written);
+int dkg_wire_decode_rows(const uint8_t* buf, size_t len, int limbs, uint32_t* rows,
+                         size_t capacity_rows, size_t* count_out, size_t* consumed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ EXPORTS = [
     "dkg_combine_batch", "dkg_combine_batch_device",
     "dkg_encrypt_batch", "dkg_modexp_grouped",
     "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve", "dkg_biprime_verdict",
+    "dkg_wire_encode_rows", "dkg_wire_decode_rows",
 ]
 
 
@@ -76,6 +77,9 @@ def _load() -> ctypes.CDLL:
     lib.dkg_jacobi_batch.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_void, ctypes.c_size_t, ctypes.c_int]
     lib.dkg_small_prime_sieve.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u8p, ctypes.c_size_t, ctypes.c_int]
     lib.dkg_biprime_verdict.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, ctypes.c_int, c_u8p, ctypes.c_size_t, ctypes.c_int]
+    c_sizep = ctypes.POINTER(ctypes.c_size_t)
+    lib.dkg_wire_encode_rows.argtypes = [c_u32p, ctypes.c_size_t, ctypes.c_int, c_u8p, ctypes.c_size_t, c_sizep]
+    lib.dkg_wire_decode_rows.argtypes = [c_u8p, ctypes.c_size_t, ctypes.c_int, c_u32p, ctypes.c_size_t, c_sizep, c_sizep]
     return lib
 
 

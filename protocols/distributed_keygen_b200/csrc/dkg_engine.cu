@@ -360,6 +360,10 @@ extern "C" {
 int dkg_version(void) { return 100; }
 
 const char* dkg_last_error(void) { return g_err.c_str(); }
+}
+// error text for the host-only translation units (dkg_wire.cu)
+void dkg_set_error(const char* msg) { g_err = msg; }
+extern "C" {
 
 int dkg_device_count(int* count) {
   if (!count) return fail(DKG_ERR_INVALID, "null count");

@@ -154,3 +154,38 @@ def decrypt_sequence_local(
     dicts = [{pid: partials[pid][i] for pid in keys} for i in range(len(ciphertexts))]
     key = keys[combiner if combiner is not None else min(keys)]
     return key.decrypt_batch(dicts)
+
+
+def partial_decryption_message(key: PaillierSharedKey, ciphertext_rows: np.ndarray) -> bytes:
+    """Loop 1 of ``_decrypt_sequence_raw`` plus the body of its broadcast (``:463-484``) with no
+    Python int in between: ciphertext limb rows -> batched partial decryption -> message bytes
+    (``wire.pack_partial_decryption_message``).  ``ZeroDivisionError`` if a ciphertext is not a
+    unit and the exponent is negative, as ``mod_inv`` raises in the reference."""
+    from . import wire
+
+    rows, status = key.partial_decrypt_limbs(ciphertext_rows)
+    if status.any():
+        raise ZeroDivisionError("ciphertext not invertible modulo N^2")
+    return wire.pack_partial_decryption_message(rows)
+
+
+def decrypt_from_messages(key: PaillierSharedKey, messages: Mapping[int, bytes]) -> np.ndarray:
+    """The receive side (``:497-515``): one message body per party index -> plaintext limb rows
+    [count][limbs(N)].  Indexing parties 1..degree+1 raises ``KeyError`` for a missing one
+    (``paillier_shared_key.py:108-110``); a failed divisibility check raises the reference's
+    ``ValueError`` (``:119-123``)."""
+    from . import wire
+    from .paillier_shared_key import n_square_limbs
+
+    l2 = n_square_limbs(key.n)
+    shares = key.share.degree + 1
+    parts = [wire.unpack_partial_decryption_message(messages[i + 1], l2) for i in range(shares)]
+    if len({p.shape[0] for p in parts}) != 1:
+        raise ValueError("partial decryption messages of different lengths")
+    out, status = key.decrypt_limbs(np.stack(parts))
+    if status.any():
+        raise ValueError(
+            "Combined decryption minus one is not divisible by N. This might be caused by the "
+            "fact that the ciphertext that is being decrypted, differs between the parties."
+        )
+    return out

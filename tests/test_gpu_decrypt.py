@@ -102,3 +102,40 @@ def test_decrypt_sequence_roundtrip_cfg1():
     assert keys[2].decrypt_batch(dicts) == [m % dk.n for m in ms]
     for key in keys.values():
         key.close()
+
+
+def test_decrypt_through_wire_messages(dealer_vectors):
+    """Section 8 f4: ciphertext limb rows -> partial decryption -> message bytes -> combination,
+    no Python int on the way; bytes equal a generic msgpack serialisation of the oracle's values
+    with the reference's big-integer tagging, plaintexts equal the reference's."""
+    import msgpack
+    from oracle import keys as okeys
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+    from protocols.distributed_keygen_b200.paillier_shared_key import n_square_limbs
+
+    item = dealer_vectors["keys"]["cfg2_k2048_p3_t1_real"]
+    dk = okeys.dealer_key_from_json(item["key"])
+    keys = _gpu_keys(dk.keys)
+    good = [v for v in item["vectors"] if "error" not in v]
+    cs = [_h(v["c"]) for v in good]
+    rows = ints_to_limbs(cs, n_square_limbs(dk.n))
+    messages = {pid: dkg.partial_decryption_message(key, rows) for pid, key in keys.items()}
+    for pid in keys:
+        want = [_h(v["partials"][str(pid)]) for v in good]
+        generic = msgpack.packb(
+            {"content": "partial_decryption_sequence",
+             "value": [{"type": "int", "data": w.to_bytes((w.bit_length() + 8) // 8, "little", signed=True)} for w in want]},
+            use_bin_type=True)
+        assert messages[pid] == generic
+    out = dkg.decrypt_from_messages(keys[3], messages)
+    assert limbs_to_ints(out) == [_h(v["plaintext"]) for v in good]
+    with pytest.raises(KeyError):
+        dkg.decrypt_from_messages(keys[1], {1: messages[1], 3: messages[3]})
+    tampered = dict(messages)
+    other = ints_to_limbs([c + 1 for c in cs], n_square_limbs(dk.n))
+    tampered[2] = dkg.partial_decryption_message(keys[2], other)
+    with pytest.raises(ValueError, match="not divisible by N"):
+        dkg.decrypt_from_messages(keys[1], tampered)
+    for key in keys.values():
+        key.close()
