@@ -35,15 +35,16 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
   uint32_t* work = base32 + 2 * Lp * 32;
   const V* Ns = reinterpret_cast<const V*>(Ns32);
   const V* NIs = reinterpret_cast<const V*>(Ns32 + Lp);
-  const V* R2g = reinterpret_cast<const V*>(p.consts + Lp + K);
-  const V* R3g = reinterpret_cast<const V*>(p.consts + Lp + K + 2 * Lp);
+  // lane-replicated R^2, R, R^3 ([v][lane]) follow the uniform constants
+  const V* R2rep = reinterpret_cast<const V*>(p.consts + Lp + K + 3 * Lp) + lane;
+  const V* R3rep = R2rep + (size_t)2 * LV * 32;
   V* Qg = reinterpret_cast<V*>(p.scratch + (size_t)w * Lp * 32);
 
   WarpIO<K, M> ioX;
   ioX.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
   ioX.ns = (uint32_t)__cvta_generic_to_shared(Ns);
   ioX.nis = (uint32_t)__cvta_generic_to_shared(NIs);
-  ioX.Qg = Qg + lane; ioX.Y = nullptr; ioX.ystride = 0;
+  ioX.Qg = Qg + lane; ioX.Y = nullptr;
   WarpIO<K, M> ioX2 = ioX;
   ioX2.xs = (uint32_t)__cvta_generic_to_shared(X2w + lane);
 
@@ -69,14 +70,14 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
       }
     }
     __syncwarp();
-    ioX2.Y = R2g; ioX2.ystride = 1;
+    ioX2.Y = R2rep;
     mont_call<K, M, MONT_MUL>(ioX2);                     // c_k * R
     V* s = S(g);
     for (int v = 0; v < LV; ++v) s[(size_t)v * 32] = X2w[v * 32 + lane];
     if (k == 0) {
       for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = X2w[v * 32 + lane];
     } else {
-      ioX.Y = s; ioX.ystride = 32;
+      ioX.Y = s;
       mont_call<K, M, MONT_MUL>(ioX);                    // P_k = P_{k-1} * c_k
       V* pp = P(g);
       for (int v = 0; v < LV; ++v) pp[(size_t)v * 32] = Xw[v * 32 + lane];
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
   // X = P * R (Montgomery form); (X)^-1 = P^-1 R^-1; times R^3 / R -> P^-1 * R
   uint32_t bad = mod_inverse_lane<K, M>(reinterpret_cast<uint32_t*>(Xw) + lane * VW, Ns32, p.n0inv, work + lane);
   __syncwarp();
-  ioX.Y = R3g; ioX.ystride = 1;
+  ioX.Y = R3rep;
   mont_call<K, M, MONT_MUL>(ioX);
   p.chain_status[(size_t)w * 32 + lane] = bad;
   if (bad && p.any_bad != nullptr) atomicOr(p.any_bad, 1u);
@@ -113,10 +114,10 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
   for (int k = glen - 1; k >= 1; --k) {
     const unsigned long long g = group_of(k), gp = group_of(k - 1);
     for (int v = 0; v < LV; ++v) X2w[v * 32 + lane] = Xw[v * 32 + lane];
-    ioX2.Y = (k - 1 == 0) ? S(gp) : P(gp); ioX2.ystride = 32;
+    ioX2.Y = (k - 1 == 0) ? S(gp) : P(gp);
     mont_call<K, M, MONT_MUL>(ioX2);                     // c_k^-1 * R
     V* s = S(g);
-    ioX.Y = s; ioX.ystride = 32;
+    ioX.Y = s;
     mont_call<K, M, MONT_MUL>(ioX);                      // inv for the next step
     for (int v = 0; v < LV; ++v) s[(size_t)v * 32] = X2w[v * 32 + lane];
     if (p.plain_out != nullptr) store_plain(ioX2, X2w32, g);

@@ -47,6 +47,16 @@ constexpr Shape kShapes[] = {
 };
 
 using KernelFn = void (*)(const dkg::ModexpParams);
+
+// A CTA-uniform constant in the layout of a lane-private operand ([vector][lane], vectors of
+// VW = 4 limbs when K % 4 == 0, else 2): multiplication operands are always read with this
+// one stride (see WarpIO in dkg_modexp.cuh), so constants that get multiplied are replicated.
+void append_lane_replicated(std::vector<uint32_t>& out, const std::vector<uint32_t>& c, int K) {
+  const int VW = (K % 4 == 0) ? 4 : 2;
+  for (size_t v = 0; v < c.size() / VW; ++v)
+    for (int lane = 0; lane < 32; ++lane)
+      for (int e = 0; e < VW; ++e) out.push_back(c[v * VW + e]);
+}
 }  // namespace
 namespace dkg {
 // one per dkg_kernels_<n>.cu
@@ -411,6 +421,7 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   consts.insert(consts.end(), r2.begin(), r2.end());
   consts.insert(consts.end(), one_r.begin(), one_r.end());
   consts.insert(consts.end(), r3.begin(), r3.end());
+  for (const dkg_host::Limbs* v : {&r2, &one_r, &r3}) append_lane_replicated(consts, *v, K);
 
   // window digits
   ctx->ebits = exp_limbs ? dkg_host::bit_length(exponent, exp_limbs) : 0;
@@ -550,6 +561,7 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
   plain1[0] = 1;
   std::vector<uint32_t> kc;
   for (const dkg_host::Limbs* v : {&N, &ninv, &dneg, &r2a, &r2b, &onea, &oneb, &plain1, &zero}) kc.insert(kc.end(), v->begin(), v->end());
+  for (const dkg_host::Limbs* v : {&r2a, &r2b, &onea, &oneb, &plain1, &zero}) append_lane_replicated(kc, *v, K);
   std::vector<uint32_t> ioc;
   for (const dkg_host::Limbs* v : {&N, &r2_mod_n, &ninvpos}) ioc.insert(ioc.end(), v->begin(), v->end());
 

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
   io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
   io.ns = (uint32_t)__cvta_generic_to_shared(Nw + lane);
   io.nis = (uint32_t)__cvta_generic_to_shared(NIw + lane);
-  io.Qg = Qg + lane; io.Y = nullptr; io.ystride = 0;
+  io.Qg = Qg + lane; io.Y = nullptr;
 
   const unsigned long long count = p.groups * (unsigned long long)p.per_group;
   const unsigned long long nwork = (count + 31ull) / 32ull;
@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
     __syncwarp();
 
     // canonical reduction of the base is not needed: Montgomery arithmetic works on [0, R)
-    io.Y = R2l + lane; io.ystride = 32;
+    io.Y = R2l + lane;
     mont_call<K, M, MONT_MUL, true>(io);
 
     const int tsize = (1 << p.wbits) - 1;
     for (int v = 0; v < LV; ++v) tab[(size_t)v * 32 + lane] = Xw[v * 32 + lane];
     for (int d = 2; d <= tsize; ++d) {
-      io.Y = tab + lane; io.ystride = 32;
+      io.Y = tab + lane;
       mont_call<K, M, MONT_MUL, true>(io);
       V* dst = tab + (size_t)(d - 1) * LV * 32 + lane;
       for (int v = 0; v < LV; ++v) dst[(size_t)v * 32] = Xw[v * 32 + lane];
@@ -170,7 +170,6 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
         for (int s = 0; s < p.wbits; ++s) mont_call<K, M, MONT_SQR, true>(io);
       const int d = dg[t];
       io.Y = (d == 0) ? (ONEl + lane) : (tab + (size_t)(d - 1) * LV * 32 + lane);
-      io.ystride = 32;
       mont_call<K, M, MONT_MUL, true>(io);
     }
     mont_call<K, M, MONT_REDC, true>(io);

@@ -72,7 +72,12 @@ __device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t o
 //          lane are 32 vectors apart); ns/nis: the CTA-uniform modulus and block inverse;
 //  Qg      this lane's Montgomery-quotient blocks in the warp's global scratch (same
 //          vector-major / lane-minor layout; L1/L2 resident, always read through the prefetch);
-//  Y       multiplication operand in global memory at Y[v * ystride].
+//  Y       multiplication operand in global memory, this lane's vector 0; like every other
+//          lane-private array its vectors are 32 apart (uniform constants are kept lane-replicated
+//          by the host for this reason): with ONE compile-time stride the prefetch inside the block
+//          product needs no address arithmetic, only immediate offsets -- a run-time stride put
+//          64-bit adds between the multiplies and made ptxas shuffle the accumulator through
+//          ~40 IMAD.MOV per block product, all on the multiplier pipe.
 //  PLN     per-lane modulus: ns/nis then address this lane's copy of N / -N^-1 (32 vectors apart),
 //          as in the grouped kernel where every lane may have its own modulus.
 template <int K, int M, bool PLN = false>
@@ -85,11 +90,12 @@ struct WarpIO {
   uint32_t xs, ns, nis;
   V* Qg;
   const V* Y;
-  int ystride;
   uint32_t ss = 0;          // second shared-memory operand S (pair arithmetic), lane's vector 0
-  const V* Y2 = nullptr;    // second global operand
-  int y2stride = 0;
+  const V* Y2 = nullptr;    // second global operand (same layout as Y)
 
+  // never true (a shared-space address is far below 2^32 - 1), but not provably so: guards the
+  // pipe-balance ballast in mont_mul
+  __device__ __forceinline__ bool never() const { return ns == 0xffffffffu; }
   __device__ __forceinline__ void load_x(int i, uint32_t (&r)[K]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, xs + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
@@ -100,7 +106,7 @@ struct WarpIO {
   }
   __device__ __forceinline__ void load_y(int j, uint32_t (&r)[K]) const {
 #pragma unroll
-    for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Y + (size_t)(j * KV + q) * ystride); unpack(v, &r[q * VW]); }
+    for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Y + (size_t)(j * KV + q) * 32); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_q(int i, uint32_t (&r)[K]) const {
 #pragma unroll
@@ -109,21 +115,18 @@ struct WarpIO {
   // Prefetch descriptor: the next y operand comes either from shared memory (an X block) or from
   // global memory (table entry / quotient block).  Two predicated loads, exactly one of which is
   // on, keep the block product branch-free without going through generic addressing.
-  struct Prefetch { const char* gbase; uint32_t gstride; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
+  struct Prefetch { const char* gbase; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
     d.on_s = (kind == PAIR_XX || kind == PAIR_XS) ? 1u : 0u;
     d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
     d.sbase = (kind == PAIR_XS ? ss : xs) + (uint32_t)(blk * KV) * 32u * VB;
-    const char* yg = reinterpret_cast<const char*>(Y + (size_t)(blk * KV) * ystride);
-    const char* y2g = reinterpret_cast<const char*>(Y2 + (size_t)(blk * KV) * y2stride);
-    const char* qg = reinterpret_cast<const char*>(Qg + (size_t)(blk * KV) * 32);
-    d.gbase = kind == PAIR_XY ? yg : (kind == PAIR_SY2 ? y2g : qg);
-    d.gstride = kind == PAIR_XY ? (uint32_t)ystride * VB : (kind == PAIR_SY2 ? (uint32_t)y2stride * VB : 32u * VB);
+    const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : Qg);
+    d.gbase = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
     return d;
   }
   __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
-    ld_pred2(&r[v * VW], d.gbase + (size_t)v * d.gstride, d.on_g, d.sbase + (uint32_t)v * 32u * VB, d.on_s, V());
+    ld_pred2(&r[v * VW], d.gbase + (size_t)v * 32u * VB, d.on_g, d.sbase + (uint32_t)v * 32u * VB, d.on_s, V());
   }
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
 #pragma unroll
@@ -271,8 +274,10 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
   uint32_t* Xw32 = reinterpret_cast<uint32_t*>(Xw);
   const V* Ns = reinterpret_cast<const V*>(Ns32);
   const V* NIs = reinterpret_cast<const V*>(Ns32 + Lp);
-  const V* R2g = reinterpret_cast<const V*>(p.consts + Lp + K);
   const V* ONEg = reinterpret_cast<const V*>(p.consts + Lp + K + Lp);
+  // lane-replicated copies of R^2 and R mod N ([v][lane], after the uniform constants)
+  const V* R2rep = reinterpret_cast<const V*>(p.consts + Lp + K + 3 * Lp) + lane;
+  const V* ONErep = R2rep + (size_t)LV * 32;
 
   const unsigned gwarp = blockIdx.x * nwarps + warp;
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
   io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
   io.ns = (uint32_t)__cvta_generic_to_shared(Ns);
   io.nis = (uint32_t)__cvta_generic_to_shared(NIs);
-  io.Qg = Qg + lane; io.Y = nullptr; io.ystride = 0;
+  io.Qg = Qg + lane; io.Y = nullptr;
 
   const unsigned long long ngroups = (p.count + 31ull) / 32ull;
   for (;;) {
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
 
     // ---- to Montgomery form: X <- X * R^2 / R ------------------------------------------------
     if (!in_mont_form) {
-      io.Y = R2g; io.ystride = 1;
+      io.Y = R2rep;
       mont_call<K, M, MONT_MUL>(io);
     }
 
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
       const int tsize = (1 << p.wbits) - 1;
       for (int v = 0; v < LV; ++v) tab[(size_t)v * 32 + lane] = Xw[v * 32 + lane];
       for (int d = 2; d <= tsize; ++d) {
-        io.Y = tab + lane; io.ystride = 32;
+        io.Y = tab + lane;
         mont_call<K, M, MONT_MUL>(io);
         V* dst = tab + (size_t)(d - 1) * LV * 32 + lane;
         for (int v = 0; v < LV; ++v) dst[(size_t)v * 32] = Xw[v * 32 + lane];
@@ -348,8 +353,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
       for (int t = 1; t < p.ndigits; ++t) {
         for (int s = 0; s < p.wbits; ++s) mont_call<K, M, MONT_SQR>(io);
         const int d = p.digits[t];
-        if (d == 0) { io.Y = ONEg; io.ystride = 1; }
-        else { io.Y = tab + (size_t)(d - 1) * LV * 32 + lane; io.ystride = 32; }
+        io.Y = d == 0 ? ONErep : tab + (size_t)(d - 1) * LV * 32 + lane;
         mont_call<K, M, MONT_MUL>(io);
       }
     }
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
         }
       }
       __syncwarp();
-      io.Y = tab + lane; io.ystride = 32;
+      io.Y = tab + lane;
       mont_call<K, M, MONT_MUL>(io);   // (x R) * y / R = x y
     } else {
       mont_call<K, M, MONT_REDC>(io);

@@ -27,6 +27,29 @@ namespace dkg {
 //   MULADD: X <- (X * Y + S * Y2) * R^-1   (Y, Y2 in global memory)
 enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2, MONT_MUL2S = 3, MONT_MULADD = 4 };
 
+// Pipe-balance ballast.  ptxas decides per FUNCTION, from static instruction counts and blind to
+// loop depth, on which pipe the register moves and single carry adds of the whole function go:
+// ALU (MOV, IADD3.X) or the multiplier pipe (IMAD.MOV.U32, IMAD.X).  The merge/shift/subtract code
+// around the block product is ALU-heavy, so without help it sends ~70 moves and ~15 carry adds per
+// block product to the multiplier pipe -- the one pipe this kernel saturates (measured: 16 % of
+// its cycles, profiles/r01_ncu_nsq_source_opcodes.txt).  A block of FFMAs that is never executed
+// (guarded by io.never(), a run-time condition that is never true) tips the static balance, and every one of those instructions
+// moves to the idle ALU pipe.  It costs code bytes that are never fetched.
+#ifndef DKG_PIPE_BALLAST
+#define DKG_PIPE_BALLAST 3072
+#endif
+DKG_HD uint32_t pipe_ballast(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  float f = __uint_as_float(a);
+  const float g = __uint_as_float(b);
+#pragma unroll
+  for (int q = 0; q < DKG_PIPE_BALLAST; q++) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f) : "f"(g));
+  return __float_as_uint(f);
+#else
+  return a ^ b;
+#endif
+}
+
 // Column accumulator of the block product scan, kept in a carry-save form so that a K x K block
 // multiply-accumulate is nothing but IMAD.WIDE carry chains:
 //   value = E + (O << 32) + sum_k CE[k] << 32(K+2k) + sum_k CO[k] << 32(K+2k+1)
@@ -36,8 +59,8 @@ enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2, MONT_MUL2S = 3, MONT_
 // the inner loop.  `merge` folds everything back into E (once or twice per column).
 template <int K>
 struct ColAcc {
-  uint32_t E[2 * K + 2];
-  uint32_t O[2 * K - 2];
+  uint64_t E[K + 1];   // limbs (2p, 2p+1)
+  uint64_t O[K - 1];   // limbs (2p+1, 2p+2)
   uint32_t CE[K / 2 + 1];
   uint32_t CO[K / 2];
 };
@@ -45,7 +68,7 @@ struct ColAcc {
 template <int K>
 DKG_HD void acc_clear_side(ColAcc<K>& a) {
 #pragma unroll
-  for (int i = 0; i < 2 * K - 2; i++) a.O[i] = 0;
+  for (int i = 0; i < K - 1; i++) a.O[i] = 0;
 #pragma unroll
   for (int i = 0; i < K / 2 + 1; i++) a.CE[i] = 0;
 #pragma unroll
@@ -78,22 +101,22 @@ DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], co
 #pragma unroll
   for (int j = 0; j < K; j++) {
     if ((j & 1) == 0) {
-      mad_cc(a.E[j], a.E[j + 1], x[0], y[j]);
+      mad_cc64(a.E[j / 2], x[0], y[j]);
 #pragma unroll
-      for (int i = 2; i < K; i += 2) madc_cc(a.E[i + j], a.E[i + j + 1], x[i], y[j]);
+      for (int i = 2; i < K; i += 2) madc_cc64(a.E[(i + j) / 2], x[i], y[j]);
       addc(a.CE[j / 2], 0);  // limb j+K
-      mad_cc(a.O[j], a.O[j + 1], x[1], y[j]);
+      mad_cc64(a.O[j / 2], x[1], y[j]);
 #pragma unroll
-      for (int i = 3; i < K; i += 2) madc_cc(a.O[i + j - 1], a.O[i + j], x[i], y[j]);
+      for (int i = 3; i < K; i += 2) madc_cc64(a.O[(i + j - 1) / 2], x[i], y[j]);
       addc(a.CO[j / 2], 0);  // O limb j+K
     } else {
-      mad_cc(a.E[j + 1], a.E[j + 2], x[1], y[j]);
+      mad_cc64(a.E[(j + 1) / 2], x[1], y[j]);
 #pragma unroll
-      for (int i = 3; i < K; i += 2) madc_cc(a.E[i + j], a.E[i + j + 1], x[i], y[j]);
+      for (int i = 3; i < K; i += 2) madc_cc64(a.E[(i + j) / 2], x[i], y[j]);
       addc(a.CE[(j + 1) / 2], 0);  // limb j+K+1
-      mad_cc(a.O[j - 1], a.O[j], x[0], y[j]);
+      mad_cc64(a.O[(j - 1) / 2], x[0], y[j]);
 #pragma unroll
-      for (int i = 2; i < K; i += 2) madc_cc(a.O[i + j - 1], a.O[i + j], x[i], y[j]);
+      for (int i = 2; i < K; i += 2) madc_cc64(a.O[(i + j - 1) / 2], x[i], y[j]);
       addc(a.CO[(j - 1) / 2], 0);  // O limb j+K-1
     }
     // one predicated load, no branch: the block product stays a single basic block
@@ -101,24 +124,36 @@ DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], co
   }
 }
 
-// fold O, CE, CO into E and clear them
+// e <- everything folded together (2K+2 limbs); O, CE, CO cleared.  a.E is left stale: the caller
+// edits e and hands it back with acc_load.
 template <int K>
-DKG_HD void acc_merge(ColAcc<K>& a) {
-  add_cc(a.E[1], a.O[0]);
+DKG_HD void acc_merge(ColAcc<K>& a, uint32_t (&e)[2 * K + 2]) {
+  uint32_t o[2 * K - 2];
 #pragma unroll
-  for (int p = 1; p < 2 * K - 2; p++) addc_cc(a.E[p + 1], a.O[p]);
-  addc_cc(a.E[2 * K - 1], 0);
-  addc_cc(a.E[2 * K], 0);
-  addc(a.E[2 * K + 1], 0);
-  add_cc(a.E[K], a.CE[0]);
+  for (int p = 0; p < K + 1; p++) { e[2 * p] = (uint32_t)a.E[p]; e[2 * p + 1] = (uint32_t)(a.E[p] >> 32); }
+#pragma unroll
+  for (int p = 0; p < K - 1; p++) { o[2 * p] = (uint32_t)a.O[p]; o[2 * p + 1] = (uint32_t)(a.O[p] >> 32); }
+  add_cc(e[1], o[0]);
+#pragma unroll
+  for (int p = 1; p < 2 * K - 2; p++) addc_cc(e[p + 1], o[p]);
+  addc_cc(e[2 * K - 1], 0);
+  addc_cc(e[2 * K], 0);
+  addc(e[2 * K + 1], 0);
+  add_cc(e[K], a.CE[0]);
 #pragma unroll
   for (int k = 0; k < K / 2; k++) {
-    if (k > 0) addc_cc(a.E[K + 2 * k], a.CE[k]);
-    addc_cc(a.E[K + 2 * k + 1], a.CO[k]);
+    if (k > 0) addc_cc(e[K + 2 * k], a.CE[k]);
+    addc_cc(e[K + 2 * k + 1], a.CO[k]);
   }
-  addc_cc(a.E[2 * K], a.CE[K / 2]);
-  addc(a.E[2 * K + 1], 0);
+  addc_cc(e[2 * K], a.CE[K / 2]);
+  addc(e[2 * K + 1], 0);
   acc_clear_side<K>(a);
+}
+
+template <int K>
+DKG_HD void acc_load(ColAcc<K>& a, const uint32_t (&e)[2 * K + 2]) {
+#pragma unroll
+  for (int p = 0; p < K + 1; p++) a.E[p] = ((uint64_t)e[2 * p + 1] << 32) | e[2 * p];
 }
 
 // r = x[0..K) * y mod 2^(32K)   (x is the low block of a wider array)
@@ -214,97 +249,109 @@ struct ColPlan {
 // the pair arithmetic, the two mixed products) stays inside the instruction cache.
 template <int K, int M, class IO>
 DKG_HD void mont_mul(const IO& io, const int MODE) {
+  using Plan = ColPlan<M>;
   ColAcc<K> a;
-  uint32_t Tc[K + 2];  // carry-in from the previous column (merged)
+  uint32_t e[2 * K + 2];  // 32-bit view of the accumulator at column boundaries and events
+  uint32_t Tc[K + 2];     // carry-in from the previous column (merged)
 #pragma unroll
   for (int i = 0; i < K + 2; i++) Tc[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 2 * K + 2; i++) a.E[i] = 0;
   acc_clear_side<K>(a);
 
   uint32_t xb[K], yb[K];
   // operands of the very first block product (everything after it is prefetched)
   {
-    const PairDesc d = ColPlan<M>(0, MODE).at(0, 0);
+    const PairDesc d = Plan(0, MODE).at(0, 0);
     if (d.kind == PAIR_XY) { io.load_x(d.xi, xb); io.load_y(d.yi, yb); }
     else if (d.kind == PAIR_XX) { io.load_x(d.xi, xb); io.load_x(d.yi, yb); }
     else if (d.kind == PAIR_XS) { io.load_x(d.xi, xb); io.load_s(d.yi, yb); }
   }
 
   for (int c = 0; c < 2 * M; ++c) {
-    const ColPlan<M> plan(c, MODE);
+    const Plan plan(c, MODE);
     const bool defer_carry = plan.ndouble > 0;
 
-    // seed the accumulator with the carry-in, unless it must not be doubled
+    // Seed the accumulator with the carry-in.  Where the leading products get doubled, seed with
+    // HALF the carry-in and keep its low bit aside: 2*(Tc >> 1) + (Tc & 1) = Tc after the doubling,
+    // so the K+2 carry-in limbs need not stay in registers across those block products.
+    uint32_t tc_bit = 0;
     if (!defer_carry) {
 #pragma unroll
-      for (int p = 0; p < K + 2; p++) a.E[p] = Tc[p];
+      for (int p = 0; p < K + 2; p++) e[p] = Tc[p];
     } else {
+      tc_bit = Tc[0] & 1u;
 #pragma unroll
-      for (int p = 0; p < K + 2; p++) a.E[p] = 0;
+      for (int p = 0; p < K + 1; p++) e[p] = (Tc[p] >> 1) | (Tc[p + 1] << 31);
+      e[K + 1] = Tc[K + 1] >> 1;
     }
 #pragma unroll
-    for (int p = K + 2; p < 2 * K + 2; p++) a.E[p] = 0;
+    for (int p = K + 2; p < 2 * K + 2; p++) e[p] = 0;
 
     if (MODE == MONT_REDC && c < M) {
       uint32_t tb[K];
       io.load_x(c, tb);
-      add_cc(a.E[0], tb[0]);
+      add_cc(e[0], tb[0]);
 #pragma unroll
-      for (int p = 1; p < K; p++) addc_cc(a.E[p], tb[p]);
+      for (int p = 1; p < K; p++) addc_cc(e[p], tb[p]);
 #pragma unroll
-      for (int p = K; p <= 2 * K; p++) addc_cc(a.E[p], 0);
-      addc(a.E[2 * K + 1], 0);
+      for (int p = K; p <= 2 * K; p++) addc_cc(e[p], 0);
+      addc(e[2 * K + 1], 0);
     }
-
-    for (int t = 0; t < plan.total; ++t) {
-      if ((MODE == MONT_SQR || MODE == MONT_MUL2S) && defer_carry && t == plan.ndouble) {
-        // all products that count twice are in: double them, then add the carry-in
-        acc_merge<K>(a);
+    // The column's block products run in up to three stretches separated by two events: the
+    // doubling of the cross products (squaring modes) and the quotient step.  Every stretch starts
+    // from the merged 32-bit view e (the seed, or the merge of what has been accumulated) through
+    // the SAME acc_load and runs the SAME inner loop, whose body is nothing but the block product
+    // and its operand traffic: one way in, one back edge.
+    const int t_double = ((MODE == MONT_SQR || MODE == MONT_MUL2S) && defer_carry) ? plan.ndouble : -1;
+    const int t_quot = c < M ? plan.total - 1 : -1;
+    int t = 0;
+    while (t < plan.total) {
+      if (t > 0) acc_merge<K>(a, e);
+      if (t == t_double) {
+        // all products that count twice are in (plus half the carry-in): double
 #pragma unroll
-        for (int p = 2 * K + 1; p > 0; p--) a.E[p] = (a.E[p] << 1) | (a.E[p - 1] >> 31);
-        a.E[0] <<= 1;
-        add_cc(a.E[0], Tc[0]);
-#pragma unroll
-        for (int p = 1; p < K + 2; p++) addc_cc(a.E[p], Tc[p]);
-#pragma unroll
-        for (int p = K + 2; p <= 2 * K; p++) addc_cc(a.E[p], 0);
-        addc(a.E[2 * K + 1], 0);
+        for (int p = 2 * K + 1; p > 0; p--) e[p] = (e[p] << 1) | (e[p - 1] >> 31);
+        e[0] = (e[0] << 1) | tc_bit;
       }
-      if (t == plan.total - 1 && c < M) {
+      if (t == t_quot) {
         // quotient block: Q_c = T_low * (-N^-1) mod 2^(32K); Q_c * N_0 then clears T_low
-        acc_merge<K>(a);
         io.load_ninv(yb);
-        block_mul_lo<K>(xb, a.E, yb);
+        block_mul_lo<K>(xb, e, yb);
         io.store_q(c, xb);
         io.load_n(0, yb);
       }
-      // what comes next (possibly in the next column): its y operand is prefetched behind this
-      // block product, its x operand loaded right after
-      PairDesc nx;
-      nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
-      if (t + 1 < plan.total) nx = plan.at(c, t + 1);
-      else if (c + 1 < 2 * M) {
-        const ColPlan<M> np(c + 1, MODE);
-        if (np.total > 0) nx = np.at(c + 1, 0);
+      acc_load<K>(a, e);
+      int t_end = plan.total;
+      if (t < t_double) t_end = t_double;
+      else if (t < t_quot) t_end = t_quot;
+      for (; t < t_end; ++t) {
+        // what comes next (possibly in the next column): its y operand is prefetched behind this
+        // block product, its x operand loaded right after
+        PairDesc nx;
+        nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
+        if (t + 1 < plan.total) nx = plan.at(c, t + 1);
+        else if (c + 1 < 2 * M) {
+          const Plan np(c + 1, MODE);
+          if (np.total > 0) nx = np.at(c + 1, 0);
+        }
+        block_mac<K>(a, xb, yb, io, io.prefetch_desc(nx.kind, nx.yi));
+        if (nx.kind == PAIR_XY || nx.kind == PAIR_XX || nx.kind == PAIR_XS) io.load_x(nx.xi, xb);
+        else if (nx.kind == PAIR_SY2) io.load_s(nx.xi, xb);
+        else if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
       }
-      block_mac<K>(a, xb, yb, io, io.prefetch_desc(nx.kind, nx.yi));
-      if (nx.kind == PAIR_XY || nx.kind == PAIR_XX || nx.kind == PAIR_XS) io.load_x(nx.xi, xb);
-      else if (nx.kind == PAIR_SY2) io.load_s(nx.xi, xb);
-      else if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
     }
-    acc_merge<K>(a);
+    if (plan.total > 0) acc_merge<K>(a, e);
 
     if (c >= M) {
       uint32_t ob[K];
 #pragma unroll
-      for (int p = 0; p < K; p++) ob[p] = a.E[p];
+      for (int p = 0; p < K; p++) ob[p] = e[p];
       io.store_x(c - M, ob);
     }
 #pragma unroll
-    for (int p = 0; p < K + 2; p++) Tc[p] = a.E[p + K];
+    for (int p = 0; p < K + 2; p++) Tc[p] = e[p + K];
   }
 
+  if (io.never()) Tc[0] = pipe_ballast(Tc[0], Tc[1]);
   // result = Tc[0]*R + X < R + N: subtract N once iff the carry limb is set
   const uint32_t mask = 0u - Tc[0];
   uint32_t borrow = 0;

@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
   uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
   const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
-  const V* R2A = Cg, *R2B = Cg + LV, *ONEA = Cg + 2 * LV, *ONEB = Cg + 3 * LV, *PLAIN1 = Cg + 4 * LV, *ZERO = Cg + 5 * LV;
+  const V* ONEA = Cg + 2 * LV, *ONEB = Cg + 3 * LV;
+  // the six constants again, lane-replicated ([v][lane]) so that they can be multiplication operands
+  const V* Crep = Cg + 6 * LV + lane;
+  const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
+          *ONEBr = Crep + (size_t)3 * LV * 32, *PLAIN1r = Crep + (size_t)4 * LV * 32, *ZEROr = Crep + (size_t)5 * LV * 32;
 
   const unsigned gwarp = blockIdx.x * nwarps + warp;
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
@@ -118,9 +122,9 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   io.nis = (uint32_t)__cvta_generic_to_shared(Ns32 + Lp);
   io.Qg = Qg + lane;
 
-  // (A, B) <- (A, B) * (c, d): c, d in global memory with vector stride `st`
-  auto pair_mul = [&](const V* c, const V* d, int st) {
-    io.xs = b_s; io.ss = a_s; io.Y = c; io.ystride = st; io.Y2 = d; io.y2stride = st;
+  // (A, B) <- (A, B) * (c, d): c, d in global memory, lane layout
+  auto pair_mul = [&](const V* c, const V* d) {
+    io.xs = b_s; io.ss = a_s; io.Y = c; io.Y2 = d;
     mont_call<K, M, MONT_MULADD>(io);                 // B <- REDC(B c + A d)
     io.xs = a_s;
     mont_call<K, M, MONT_MUL>(io);                    // A <- REDC(A c), quotient m in Q
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
     }
     __syncwarp();
 
-    pair_mul(R2A, R2B, 1);   // into the Montgomery domain: value c * R
+    pair_mul(R2Ar, R2Br);   // into the Montgomery domain: value c * R
     if (p.ndigits == 0) {
       for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = ONEA[v]; Bw[v * 32 + lane] = ONEB[v]; }
     } else {
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
       auto tab_b = [&](int d) -> V* { return tab + ((size_t)(d - 1) * 2 + 1) * LV * 32 + lane; };
       for (int v = 0; v < LV; ++v) { tab_a(1)[(size_t)v * 32] = Aw[v * 32 + lane]; tab_b(1)[(size_t)v * 32] = Bw[v * 32 + lane]; }
       for (int d = 2; d <= tsize; ++d) {
-        pair_mul(tab_a(1), tab_b(1), 32);
+        pair_mul(tab_a(1), tab_b(1));
         V* da = tab_a(d); V* db = tab_b(d);
         for (int v = 0; v < LV; ++v) { da[(size_t)v * 32] = Aw[v * 32 + lane]; db[(size_t)v * 32] = Bw[v * 32 + lane]; }
       }
@@ -175,11 +179,11 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
       for (int t = 1; t < p.ndigits; ++t) {
         for (int s = 0; s < p.wbits; ++s) pair_sqr();
         const int d = p.digits[t];
-        if (d == 0) pair_mul(ONEA, ONEB, 1);
-        else pair_mul(tab_a(d), tab_b(d), 32);
+        if (d == 0) pair_mul(ONEAr, ONEBr);
+        else pair_mul(tab_a(d), tab_b(d));
       }
     }
-    pair_mul(PLAIN1, ZERO, 1);   // out of the Montgomery domain: the pair now stands for the result itself
+    pair_mul(PLAIN1r, ZEROr);   // out of the Montgomery domain: the pair now stands for the result itself
     __syncwarp();
 
     for (int r = 0; r < cnt; ++r) {

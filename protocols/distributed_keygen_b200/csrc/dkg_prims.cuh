@@ -32,6 +32,17 @@ DKG_HD void madc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;"
                : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
 }
+// Same on a 64-bit typed accumulator (the aligned register pair IMAD.WIDE works on).  Typing the
+// pair as ONE value matters to ptxas: with two 32-bit registers per pair it let the halves drift
+// apart across loop back edges and re-paired ~70 registers with moves around every block product.
+DKG_HD void mad_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmad.lo.cc.u32 l, %1, %2, l;\n\t"
+               "madc.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
+}
+DKG_HD void madc_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmadc.lo.cc.u32 l, %1, %2, l;\n\t"
+               "madc.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
+}
 // lo += lo32(a*b)                     (no flags)
 DKG_HD void mad_lo(uint32_t& lo, uint32_t a, uint32_t b) {
   asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
@@ -67,6 +78,16 @@ DKG_HD void madc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
   uint64_t p = (uint64_t)a * b;
   detail::add3(lo, (uint32_t)p, detail::cf(), true);
   detail::add3(hi, (uint32_t)(p >> 32), detail::cf(), true);
+}
+DKG_HD void mad_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
+  uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
+  mad_cc(lo, hi, a, b);
+  acc = ((uint64_t)hi << 32) | lo;
+}
+DKG_HD void madc_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
+  uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
+  madc_cc(lo, hi, a, b);
+  acc = ((uint64_t)hi << 32) | lo;
 }
 DKG_HD void mad_lo(uint32_t& lo, uint32_t a, uint32_t b) { lo += a * b; }
 DKG_HD void madc_lo(uint32_t& lo, uint32_t a, uint32_t b) { lo += a * b + detail::cf(); }

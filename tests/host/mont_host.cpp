@@ -10,6 +10,7 @@ template <int K, int M>
 struct HostIO {
   uint32_t* X; const uint32_t* Y; uint32_t* Q; const uint32_t* N; const uint32_t* NI;
   const uint32_t* S = nullptr; const uint32_t* Y2 = nullptr;
+  bool never() const { return false; }
   void load_s(int i, uint32_t (&r)[K]) const { std::memcpy(r, S + i * K, K * 4); }
   void load_x(int i, uint32_t (&r)[K]) const { std::memcpy(r, X + i * K, K * 4); }
   void load_y(int j, uint32_t (&r)[K]) const { std::memcpy(r, Y + j * K, K * 4); }

@@ -124,3 +124,4 @@ def test_pair_modes_host(lib, K, M):
                               sa.ctypes.data, y2a.ctypes.data) == 0
         got = _val(xa)
         assert got < R and got % n == ((x * y + s_op * y2) * r_inv) % n, (K, M, trial, "muladd")
+
