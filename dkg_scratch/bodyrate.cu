@@ -1,0 +1,61 @@
+// How fast can w warps per SMSP drive the multiplier pipe with the block product alone?
+#include <cstdio>
+#include <vector>
+#include "../protocols/distributed_keygen_b200/csrc/dkg_modexp.cuh"
+using namespace dkg;
+template <int K, bool PREF>
+__global__ void __launch_bounds__(384, 1) body_kernel(uint32_t* out, const uint32_t* in, const int* kinds, int iters) {
+  extern __shared__ uint32_t sm[];
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) sm[i] = in[i];
+  __syncthreads();
+  using IO = WarpIO<K, 5>;
+  IO io;
+  io.xs = (uint32_t)__cvta_generic_to_shared(sm) + (threadIdx.x & 31) * 8;
+  io.ss = io.xs + 4096; io.ns = io.xs + 8192; io.nis = io.ns + 256;
+  io.Qg = (typename IO::V*)(out + 1024) + (threadIdx.x & 31);
+  io.Y = (const typename IO::V*)(in + 8192) + (threadIdx.x & 31);
+  io.Y2 = io.Y + 77;
+  ColAcc<K> a;
+#pragma unroll
+  for (int i = 0; i < K + 1; i++) a.E[i] = 0;
+  acc_clear_side<K>(a);
+  uint32_t x[K], y[K];
+  io.load_x(0, x); io.load_x(1, y);
+  for (int t = 0; t < iters; ++t) {
+    const int kind = PREF ? kinds[2 * (t & 63)] : PAIR_NONE, blk = kinds[2 * (t & 63) + 1];
+    block_mac<K>(a, x, y, io, io.prefetch_desc(kind, blk));
+    if (kind == PAIR_XY || kind == PAIR_XX || kind == PAIR_XS) io.load_x(blk, x);
+    else if (kind == PAIR_SY2) io.load_s(blk, x);
+    else if (kind == PAIR_NQ) io.load_n(blk, x);
+  }
+  uint32_t e[2 * K + 2];
+  acc_merge<K>(a, e);
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * K + 2; i++) s ^= e[i];
+  if (iters == -12345) s = pipe_ballast(s, s + 1);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int main() {
+  uint32_t *in, *out; int* kinds;
+  cudaMalloc(&in, 1 << 22); cudaMalloc(&out, 1 << 22); cudaMalloc(&kinds, 1024);
+  cudaMemset(in, 0x5a, 1 << 22);
+  std::vector<int> hk(128);
+  for (int i = 0; i < 64; ++i) { hk[2 * i] = (i % 3 == 0) ? PAIR_NQ : (i % 3 == 1 ? PAIR_XX : PAIR_XY); hk[2 * i + 1] = i % 5; }
+  cudaMemcpy(kinds, hk.data(), 512, cudaMemcpyHostToDevice);
+  const int iters = 20000;
+  auto run = [&](auto kern, const char* name, int threads) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    kern<<<148, threads, 65536>>>(out, in, kinds, 100);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    kern<<<148, threads, 65536>>>(out, in, kinds, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double macs = 148.0 * threads * iters * 196.0;
+    printf("%s threads %3d: %.2f ms  %.2f T wide-MAC/s  err=%s\n", name, threads, ms, macs / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
+  };
+  for (int th : {128, 256, 384}) run(body_kernel<14, false>, "no-prefetch", th);
+  for (int th : {128, 256, 384}) run(body_kernel<14, true>, "prefetch   ", th);
+  return 0;
+}

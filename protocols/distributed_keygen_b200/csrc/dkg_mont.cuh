@@ -35,6 +35,9 @@ enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2, MONT_MUL2S = 3, MONT_
 // its cycles, profiles/r01_ncu_nsq_source_opcodes.txt).  A block of FFMAs that is never executed
 // (guarded by io.never(), a run-time condition that is never true) tips the static balance, and every one of those instructions
 // moves to the idle ALU pipe.  It costs code bytes that are never fetched.
+#ifndef DKG_INPLACE_DOUBLE
+#define DKG_INPLACE_DOUBLE 0
+#endif
 #ifndef DKG_PIPE_BALLAST
 #define DKG_PIPE_BALLAST 3072
 #endif
@@ -148,6 +151,37 @@ DKG_HD void acc_merge(ColAcc<K>& a, uint32_t (&e)[2 * K + 2]) {
   addc_cc(e[2 * K], a.CE[K / 2]);
   addc(e[2 * K + 1], 0);
   acc_clear_side<K>(a);
+}
+
+// a <- 2*a + bit, component by component (the carry-save form is linear): no merge, no carry
+// chain, every shift independent of the others.  The bit leaving the top of O has the weight of
+// the last CO counter; E has two limbs of headroom.
+template <int K>
+DKG_HD void acc_double(ColAcc<K>& a, uint32_t bit) {
+#pragma unroll
+  for (int k = 0; k < K / 2 + 1; k++) a.CE[k] <<= 1;
+#pragma unroll
+  for (int k = 0; k < K / 2; k++) a.CO[k] <<= 1;
+  a.CO[K / 2 - 1] += (uint32_t)(a.O[K - 2] >> 63);
+#pragma unroll
+  for (int p = K - 2; p > 0; p--) a.O[p] = (a.O[p] << 1) | (a.O[p - 1] >> 63);
+  a.O[0] <<= 1;
+#pragma unroll
+  for (int p = K; p > 0; p--) a.E[p] = (a.E[p] << 1) | (a.E[p - 1] >> 63);
+  a.E[0] = (a.E[0] << 1) | bit;
+}
+
+// low block of the accumulated value: (E + (O << 32)) mod 2^(32K); a is not modified
+template <int K>
+DKG_HD void acc_low(const ColAcc<K>& a, uint32_t (&tl)[K]) {
+#pragma unroll
+  for (int p = 0; p < K / 2; p++) { tl[2 * p] = (uint32_t)a.E[p]; tl[2 * p + 1] = (uint32_t)(a.E[p] >> 32); }
+  add_cc(tl[1], (uint32_t)a.O[0]);
+#pragma unroll
+  for (int p = 2; p < K; p++) {
+    const uint32_t o = (p & 1) ? (uint32_t)a.O[(p - 1) / 2] : (uint32_t)(a.O[(p - 2) / 2] >> 32);
+    if (p < K - 1) addc_cc(tl[p], o); else addc(tl[p], o);
+  }
 }
 
 template <int K>
@@ -297,29 +331,39 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
       addc(e[2 * K + 1], 0);
     }
     // The column's block products run in up to three stretches separated by two events: the
-    // doubling of the cross products (squaring modes) and the quotient step.  Every stretch starts
-    // from the merged 32-bit view e (the seed, or the merge of what has been accumulated) through
-    // the SAME acc_load and runs the SAME inner loop, whose body is nothing but the block product
-    // and its operand traffic: one way in, one back edge.
+    // doubling of the cross products (squaring modes; done in place on the carry-save form) and the
+    // quotient step (which needs the merged low block).  All stretches run the SAME inner loop,
+    // whose body is nothing but the block product and its operand traffic; the accumulator enters
+    // it from the 32-bit view e through the SAME acc_load (column start and quotient step).
     const int t_double = ((MODE == MONT_SQR || MODE == MONT_MUL2S) && defer_carry) ? plan.ndouble : -1;
     const int t_quot = c < M ? plan.total - 1 : -1;
     int t = 0;
     while (t < plan.total) {
-      if (t > 0) acc_merge<K>(a, e);
+#if DKG_INPLACE_DOUBLE
+      // all products that count twice are in (plus half the carry-in): double, in place
+      if (t == t_double) acc_double<K>(a, tc_bit);
+      if (t == 0) acc_load<K>(a, e);
+#else
       if (t == t_double) {
         // all products that count twice are in (plus half the carry-in): double
+        acc_merge<K>(a, e);
 #pragma unroll
         for (int p = 2 * K + 1; p > 0; p--) e[p] = (e[p] << 1) | (e[p - 1] >> 31);
         e[0] = (e[0] << 1) | tc_bit;
       }
+      if (t == 0 || t == t_double) acc_load<K>(a, e);
+#endif
       if (t == t_quot) {
-        // quotient block: Q_c = T_low * (-N^-1) mod 2^(32K); Q_c * N_0 then clears T_low
+        // quotient block: Q_c = T_low * (-N^-1) mod 2^(32K); Q_c * N_0 then clears T_low.  T_low
+        // needs only the low blocks of E and O (the counters weigh 2^(32K) and more), so the
+        // accumulator itself stays as it is, in carry-save form.
+        uint32_t tl[K];
+        acc_low<K>(a, tl);
         io.load_ninv(yb);
-        block_mul_lo<K>(xb, e, yb);
+        block_mul_lo<K>(xb, tl, yb);
         io.store_q(c, xb);
         io.load_n(0, yb);
       }
-      acc_load<K>(a, e);
       int t_end = plan.total;
       if (t < t_double) t_end = t_double;
       else if (t < t_quot) t_end = t_quot;
