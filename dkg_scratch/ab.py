@@ -22,4 +22,4 @@ for _ in range(2):
 from protocols.distributed_keygen_b200.limbs import limbs_to_ints
 out = d_out.cpu().numpy().view(np.uint32)
 ok = all(limbs_to_ints(out[i:i+1])[0] == pow(limbs_to_ints(host[i:i+1])[0], e, key.n_square) for i in (0, 77, B - 1))
-print(os.environ.get("TAG", ""), name, "pid", pid, "neg" if e < 0 else "pos", "B", B, "%.1f ms %.0f /s" % (best, B / best * 1e3), "ok" if ok else "MISMATCH")
+print(os.environ.get("TAG", ""), "w", info["window_bits"], "nmul", info["windows"], name, "pid", pid, "neg" if e < 0 else "pos", "B", B, "%.1f ms %.0f /s" % (best, B / best * 1e3), "ok" if ok else "MISMATCH")

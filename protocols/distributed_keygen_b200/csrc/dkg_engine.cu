@@ -193,7 +193,7 @@ struct dkg_modexp_ctx {
   int limbs = 0;  // caller-visible row width
   Shape shape{};
   int Lp = 0;
-  int wbits = 1, ndigits = 0, ebits = 0;
+  int wbits = 1, nops = 0, tab_entries = 0, nmul = 0, ebits = 0;
   int negative = 0;
   uint32_t n0inv = 0;
   int warps = 1, ctas = 1;
@@ -205,7 +205,7 @@ struct dkg_modexp_ctx {
   int inv_warps = 1;
   size_t inv_smem = 0;
   uint32_t* d_consts = nullptr;
-  uint8_t* d_digits = nullptr;
+  uint32_t* d_ops = nullptr;
   // pair arithmetic modulo N when the modulus is N^2 with known N (dkg_nsq.cuh)
   bool nsq = false;
   Shape nshape{};
@@ -231,6 +231,52 @@ int choose_window(int ebits) {
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
   }
   return best;
+}
+
+// Sliding windows for the fixed-exponent contexts.  The exponent belongs to the key, so the whole
+// batch shares ONE operation list, built here once: "square nsq times, then multiply by the odd
+// power table[idx]".  Table: c^1, c^3, ..., c^(2^w - 1), i.e. 2^(w-1) entries from one squaring and
+// 2^(w-1) - 1 multiplications; a window of w bits costs a multiplication only every ~w+1 bits.
+// op = (nsq << 8) | idx, idx 0xff = no multiplication (trailing zeros); the first op has nsq = 0
+// and means "start from table[idx]".
+constexpr uint32_t kOpNoMul = 0xffu;
+int choose_sliding_window(int ebits) {
+  if (const char* f = getenv("DKG_FORCE_WINDOW")) {  // tuning/debug knob
+    int w = atoi(f);
+    if (w >= 1 && w <= 7) return w;
+  }
+  int best = 1;
+  long best_cost = -1;
+  for (int w = 1; w <= 7; ++w) {
+    long cost = (1L << (w - 1)) + ebits / (w + 1);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
+  }
+  return best;
+}
+std::vector<uint32_t> sliding_window_ops(const uint32_t* e, int ebits, int w, int* table_entries, int* nmul) {
+  auto bit = [&](int i) { return (e[i / 32] >> (i % 32)) & 1u; };
+  std::vector<uint32_t> ops;
+  int maxidx = -1, muls = 0;
+  uint32_t pending = 0;
+  int i = ebits - 1;
+  while (i >= 0) {
+    if (!bit(i)) { ++pending; --i; continue; }
+    int l = std::max(i - w + 1, 0);
+    while (!bit(l)) ++l;
+    uint32_t v = 0;
+    for (int b = i; b >= l; --b) v = (v << 1) | bit(b);
+    const uint32_t idx = (v - 1) / 2;
+    const uint32_t nsq = ops.empty() ? 0u : pending + (uint32_t)(i - l + 1);
+    ops.push_back((nsq << 8) | idx);
+    maxidx = std::max(maxidx, (int)idx);
+    ++muls;
+    pending = 0;
+    i = l - 1;
+  }
+  if (pending) ops.push_back((pending << 8) | kOpNoMul);
+  *table_entries = maxidx + 1;
+  *nmul = muls;
+  return ops;
 }
 
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
@@ -274,7 +320,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
     p.inv_mont = b.chain_s; p.chain_status = b.chain_status; p.nchain_warps = nchain;
   }
   p.bases = d_bases; p.out = d_out; p.status = d_status; p.count = count; p.in_limbs = ctx->limbs;
-  p.consts = ctx->d_consts; p.digits = ctx->d_digits; p.ndigits = ctx->ndigits; p.wbits = ctx->wbits;
+  p.consts = ctx->d_consts; p.ops = ctx->d_ops; p.nops = ctx->nops; p.tab_entries = ctx->tab_entries;
   p.negative = ctx->negative; p.n0inv = ctx->n0inv; p.scratch = d->scratch;
   p.scratch_per_warp = ctx->scratch_per_warp; p.scratch_q_offset = ctx->scratch_q_offset; p.counter = d->counter; p.final_mul = d_final_mul;
   ctx->kernel<<<ctas, ctx->warps * 32, ctx->smem, stream>>>(p);
@@ -337,8 +383,8 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   dkg::nsq_entry_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(e);
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::NsqParams q{};
-  q.pairs_in = pairs; q.pairs_out = pairs; q.count = count; q.consts = ctx->d_nconsts; q.digits = ctx->d_digits;
-  q.ndigits = ctx->ndigits; q.wbits = ctx->wbits; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
+  q.pairs_in = pairs; q.pairs_out = pairs; q.count = count; q.consts = ctx->d_nconsts; q.ops = ctx->d_ops;
+  q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
   q.scratch_q_offset = ctx->nscratch_q_offset; q.counter = d->counter;
   ctx->nsq_kernel<<<ctas, ctx->nwarps * 32, ctx->nsmem, stream>>>(q);
   dkg::NsqIoParams x = e;
@@ -425,18 +471,10 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
 
   // window digits
   ctx->ebits = exp_limbs ? dkg_host::bit_length(exponent, exp_limbs) : 0;
-  ctx->wbits = choose_window(ctx->ebits);
-  ctx->ndigits = (ctx->ebits + ctx->wbits - 1) / ctx->wbits;
-  std::vector<uint8_t> digits(std::max(ctx->ndigits, 1), 0);
-  for (int t = 0; t < ctx->ndigits; ++t) {
-    const int lowbit = ctx->wbits * (ctx->ndigits - 1 - t);
-    unsigned dgt = 0;
-    for (int b = 0; b < ctx->wbits; ++b) {
-      const int bit = lowbit + b;
-      if (bit < ctx->ebits && ((exponent[bit / 32] >> (bit % 32)) & 1u)) dgt |= 1u << b;
-    }
-    digits[t] = (uint8_t)dgt;
-  }
+  ctx->wbits = choose_sliding_window(ctx->ebits);
+  std::vector<uint32_t> ops = sliding_window_ops(exponent, ctx->ebits, ctx->wbits, &ctx->tab_entries, &ctx->nmul);
+  ctx->nops = (int)ops.size();
+  if (ops.empty()) ops.push_back(0);
 
   // launch geometry: one CTA per SM, as many warps as shared memory allows (<= 8)
   const size_t uni = (((size_t)(Lp + K) * 4 + 15) / 16) * 16;
@@ -446,7 +484,7 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   ctx->warps = warps;
   ctx->ctas = dev->sm_count;
   ctx->smem = uni + per_warp * warps;
-  const size_t tsize = ((size_t)1 << ctx->wbits) - 1;
+  const size_t tsize = (size_t)ctx->tab_entries + 1;  // odd powers, then the slot of c^2
   // per-warp scratch: window table (also the workspace of the modular inverse: 4 arrays), then Q
   ctx->scratch_q_offset = std::max<size_t>(tsize, 4) * (size_t)Lp * 32;
   ctx->scratch_per_warp = ctx->scratch_q_offset + (size_t)Lp * 32;
@@ -465,9 +503,9 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   cudaError_t e = cudaFuncSetAttribute((const void*)ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem);
   if (e != cudaSuccess) { delete ctx; return fail(DKG_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   e = cudaMalloc(&ctx->d_consts, consts.size() * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_digits, digits.size());
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ops, ops.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_digits, digits.data(), digits.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_ops, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     dkg_modexp_ctx_destroy(ctx);
     return fail(DKG_ERR_CUDA, std::string("context upload: ") + cudaGetErrorString(e));
@@ -480,7 +518,7 @@ void dkg_modexp_ctx_destroy(dkg_modexp_ctx* ctx) {
   if (!ctx) return;
   if (ctx->dev) cudaSetDevice(ctx->dev->device);
   if (ctx->d_consts) cudaFree(ctx->d_consts);
-  if (ctx->d_digits) cudaFree(ctx->d_digits);
+  if (ctx->d_ops) cudaFree(ctx->d_ops);
   if (ctx->d_nconsts) cudaFree(ctx->d_nconsts);
   if (ctx->d_nio) cudaFree(ctx->d_nio);
   delete ctx;
@@ -571,7 +609,7 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
   int maxw = DKG_MAX_THREADS / 32;
   int warps = (int)std::min<size_t>(maxw, (kMaxDynSmem - uni) / per_warp);
   if (warps < 1) return DKG_OK;
-  const size_t tsize = ((size_t)1 << ctx->wbits) - 1;
+  const size_t tsize = (size_t)ctx->tab_entries + 1;  // odd powers, then the slot of c^2
   ctx->nscratch_q_offset = std::max<size_t>(tsize, 1) * 2 * (size_t)Lp * 32;
   ctx->nscratch_per_warp = ctx->nscratch_q_offset + (size_t)Lp * 32;
   cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(uni + per_warp * warps));
@@ -592,7 +630,7 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
 int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[12]) {
   if (!ctx || !info) return fail(DKG_ERR_INVALID, "null argument");
   info[0] = ctx->shape.K; info[1] = ctx->shape.M; info[2] = ctx->Lp; info[3] = ctx->wbits;
-  info[4] = ctx->ndigits; info[5] = ctx->ebits; info[6] = ctx->warps; info[7] = ctx->ctas;
+  info[4] = ctx->nmul; info[5] = ctx->ebits; info[6] = ctx->warps; info[7] = ctx->ctas;
   info[8] = ctx->nsq ? 1 : 0; info[9] = ctx->nshape.K; info[10] = ctx->nshape.M; info[11] = ctx->nwarps;
   return DKG_OK;
 }

@@ -18,9 +18,12 @@ struct ModexpParams {
   int in_limbs;
   // device constants: N[Lp] | NINV[K] | R2[Lp] | ONER[Lp] | R3[Lp]   (Lp = K*M)
   const uint32_t* consts;
-  const uint8_t* digits;   // window digits, most significant first
-  int ndigits;
-  int wbits;
+  // sliding-window operation list shared by the whole batch (built by the host, dkg_engine.cu):
+  // op = (nsq << 8) | idx: square nsq times, then multiply by table[idx] = c^(2 idx + 1)
+  // (idx 0xff: no multiplication); op 0 has nsq = 0 and starts from table[idx]
+  const uint32_t* ops;
+  int nops;
+  int tab_entries;         // odd powers to build: c^1 .. c^(2 tab_entries - 1)
   int negative;            // invert the base first
   uint32_t n0inv;          // -N^-1 mod 2^32
   uint32_t* scratch;       // per-warp table scratch

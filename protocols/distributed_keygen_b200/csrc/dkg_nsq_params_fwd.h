@@ -12,8 +12,8 @@ struct NsqParams {
   //   N | NINV[K] | DNEG (= -R mod N) | R2A | R2B (pair of R^2 mod N^2) | ONEA | ONEB (pair of R mod N^2)
   //   | PLAIN1 (= 1) | ZERO
   const uint32_t* consts;
-  const uint8_t* digits;
-  int ndigits, wbits;
+  const uint32_t* ops;        // sliding-window operation list, see ModexpParams
+  int nops, tab_entries;
   uint32_t* scratch;
   unsigned long long scratch_per_warp;   // in uint32
   unsigned long long scratch_q_offset;
