@@ -168,3 +168,27 @@ def test_ragged_batch_sizes(eng):
         bases = [rng.randrange(n) for _ in range(count)]
         assert ctx.modexp(bases) == [pow(b, e, n) for b in bases]
     ctx.close()
+
+
+def test_sliding_window_exponent_shapes(eng):
+    """Exponents that stress the operation list of the sliding windows: powers of two (only trailing
+    squarings), long zero runs (more than 255 squarings in one step), all ones (every window full),
+    alternating bits; through the generic kernel and through the pair arithmetic (N^2 with root)."""
+    rng = random.Random(77)
+    p = rng.getrandbits(130) | 1 | (1 << 129)
+    q = rng.getrandbits(130) | 1 | (1 << 129)
+    root = p * q
+    exps = [1 << 300, (1 << 300) + 1, (1 << 521) - 1, (1 << 400) | 1, int("10" * 150, 2), int("1" + "0" * 299 + "1" + "0" * 270 + "111", 2),
+            -((1 << 260) + 5)]
+    for modulus, kw in ((rng.getrandbits(520) | 1 | (1 << 519), {}), (root * root, {"root": root})):
+        bases = [1, 2, modulus - 1] + [rng.randrange(2, modulus) for _ in range(45)]
+        for e in exps:
+            ctx = eng.ModexpContext(modulus, e, **kw)
+            if e < 0:
+                import math
+                bases_e = [b for b in bases if math.gcd(b, modulus) == 1]
+                want = [pow(pow(b, -1, modulus), -e, modulus) for b in bases_e]
+            else:
+                bases_e, want = bases, [pow(b, e, modulus) for b in bases]
+            assert ctx.modexp(bases_e) == want, (modulus.bit_length(), e.bit_length(), kw.keys())
+            ctx.close()
