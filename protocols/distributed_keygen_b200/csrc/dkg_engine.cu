@@ -603,7 +603,8 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
   std::vector<uint32_t> ioc;
   for (const dkg_host::Limbs* v : {&N, &r2_mod_n, &ninvpos}) ioc.insert(ioc.end(), v->begin(), v->end());
 
-  const size_t uni = (((size_t)(2 * Lp + K) * 4 + 15) / 16) * 16;
+  const size_t uni = (((size_t)(2 * Lp + K) * 4 + 15) / 16) * 16 +
+                     (((size_t)dkg::sched_total_words_closed(sh.M) * 4 + 15) / 16) * 16;  // consts | schedule table
   const size_t per_warp = (size_t)2 * Lp * 32 * 4;
   // K = 22 needs more than 168 registers: run it with 10 warps
   int maxw = DKG_MAX_THREADS / 32;
@@ -876,9 +877,10 @@ int plan_grouped(DeviceState* d, int limbs, int ebits, size_t count, GroupedPlan
   plan->wbits = choose_window(ebits);
   plan->ndigits = std::max(1, (ebits + plan->wbits - 1) / plan->wbits);
   const size_t per_warp_smem = ((size_t)2 * plan->Lp + plan->K) * 32 * 4;
-  plan->warps = (int)std::min<size_t>(DKG_MAX_THREADS / 32, kMaxDynSmem / per_warp_smem);
+  const size_t sched_bytes = (((size_t)dkg::sched_total_words_closed(plan->shape.M) * 4 + 15) / 16) * 16;
+  plan->warps = (int)std::min<size_t>(DKG_MAX_THREADS / 32, (kMaxDynSmem - sched_bytes) / per_warp_smem);
   if (plan->warps < 1) return fail(DKG_ERR_UNSUPPORTED, "operand too wide for shared memory");
-  plan->smem = per_warp_smem * plan->warps;
+  plan->smem = sched_bytes + per_warp_smem * plan->warps;
   const size_t tsize = ((size_t)1 << plan->wbits) - 1;
   plan->q_off = std::max<size_t>(tsize, 1) * (size_t)plan->Lp * 32;
   plan->scratch_per_warp = plan->q_off + (size_t)3 * plan->Lp * 32;  // Q | R2 | ONER in lane layout

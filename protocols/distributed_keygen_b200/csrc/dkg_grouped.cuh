@@ -100,8 +100,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // schedule table (sched_total_words_closed(M) words, 16-byte padded), then
   // per warp: X[LV*32] | N[LV*32] | NINV[KV*32] vectors
-  V* Xw = reinterpret_cast<V*>(smem_raw) + (size_t)warp * (2 * LV + KV) * 32;
+  static_assert(sched_offset<M>(kSchedModes) == sched_total_words_closed(M), "schedule table size out of sync");
+  constexpr int SCHED_BYTES = (sched_total_words_closed(M) * 4 + 15) / 16 * 16;
+  fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw));
+  __syncthreads();
+  V* Xw = reinterpret_cast<V*>(smem_raw + SCHED_BYTES) + (size_t)warp * (2 * LV + KV) * 32;
   V* Nw = Xw + LV * 32;
   V* NIw = Nw + LV * 32;
   uint32_t* Xw32 = reinterpret_cast<uint32_t*>(Xw);
@@ -113,7 +118,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
   V* R2l = Qg + LV * 32;    // this warp's lanes' R^2 mod N, lane layout
   V* ONEl = R2l + LV * 32;  // and R mod N
 
-  WarpIO<K, M, true> io;
+  WarpIO<K, M, true, true> io;
+  io.sched_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
   io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
   io.ns = (uint32_t)__cvta_generic_to_shared(Nw + lane);
   io.nis = (uint32_t)__cvta_generic_to_shared(NIw + lane);
@@ -153,13 +159,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
 
     // canonical reduction of the base is not needed: Montgomery arithmetic works on [0, R)
     io.Y = R2l + lane;
-    mont_call<K, M, MONT_MUL, true>(io);
+    mont_call<K, M, MONT_MUL, true, true>(io);
 
     const int tsize = (1 << p.wbits) - 1;
     for (int v = 0; v < LV; ++v) tab[(size_t)v * 32 + lane] = Xw[v * 32 + lane];
     for (int d = 2; d <= tsize; ++d) {
       io.Y = tab + lane;
-      mont_call<K, M, MONT_MUL, true>(io);
+      mont_call<K, M, MONT_MUL, true, true>(io);
       V* dst = tab + (size_t)(d - 1) * LV * 32 + lane;
       for (int v = 0; v < LV; ++v) dst[(size_t)v * 32] = Xw[v * 32 + lane];
     }
@@ -167,12 +173,12 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
     const uint8_t* dg = p.digits + gid * (unsigned long long)p.ndigits;
     for (int t = 0; t < p.ndigits; ++t) {
       if (t > 0)
-        for (int s = 0; s < p.wbits; ++s) mont_call<K, M, MONT_SQR, true>(io);
+        for (int s = 0; s < p.wbits; ++s) mont_call<K, M, MONT_SQR, true, true>(io);
       const int d = dg[t];
       io.Y = (d == 0) ? (ONEl + lane) : (tab + (size_t)(d - 1) * LV * 32 + lane);
-      mont_call<K, M, MONT_MUL, true>(io);
+      mont_call<K, M, MONT_MUL, true, true>(io);
     }
-    mont_call<K, M, MONT_REDC, true>(io);
+    mont_call<K, M, MONT_REDC, true, true>(io);
     canonicalize<K, M>(io, 1);
     __syncwarp();
 

@@ -80,8 +80,19 @@ __device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t o
 //          ~40 IMAD.MOV per block product, all on the multiplier pipe.
 //  PLN     per-lane modulus: ns/nis then address this lane's copy of N / -N^-1 (32 vectors apart),
 //          as in the grouped kernel where every lane may have its own modulus.
-template <int K, int M, bool PLN = false>
+//  SCHED   the pair schedule comes from a table in shared memory (sched_s, filled by the kernel
+//          with fill_schedule) instead of being recomputed inside the block-product loop.
+template <int K, int M, bool PLN = false, bool SCHED_ = false>
 struct WarpIO {
+  static constexpr bool SCHED = SCHED_;
+  uint32_t sched_s = 0;     // shared-space address of the schedule table (SCHED only)
+  __device__ __forceinline__ uint32_t sched_begin(int word_offset) const { return sched_s + 4u * (uint32_t)word_offset; }
+  __device__ __forceinline__ uint32_t sched_next(uint32_t pos) const { return pos + 4u; }
+  __device__ __forceinline__ uint32_t sched_word(uint32_t base, int i) const {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + 4u * (uint32_t)i));
+    return w;
+  }
   using V = typename VecSel<K>::T;
   static constexpr int VW = VecSel<K>::VW;
   static constexpr int KV = K / VW;
@@ -103,6 +114,12 @@ struct WarpIO {
   __device__ __forceinline__ void load_s(int i, uint32_t (&r)[K]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, ss + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
+  }
+  // block i of S (from_s) or X: one load sequence for both, the base selected
+  __device__ __forceinline__ void load_xs(bool from_s, int i, uint32_t (&r)[K]) const {
+    const uint32_t base = from_s ? ss : xs;
+#pragma unroll
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, base + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
   __device__ __forceinline__ void load_y(int j, uint32_t (&r)[K]) const {
 #pragma unroll
@@ -246,13 +263,19 @@ __device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n
 
 // One out-of-line instance of the Montgomery product per shape, shared by every mode (square,
 // multiply, reduce, doubled product, multiply-add): the hot loop stays inside the instruction cache.
-template <int K, int M, bool PLN>
-__device__ __noinline__ void mont_call_rt(const WarpIO<K, M, PLN> io, const int mode) {
+template <int K, int M, bool PLN, bool SCHED>
+__device__ __noinline__ void mont_call_rt(const WarpIO<K, M, PLN, SCHED> io, const int mode) {
   mont_mul<K, M>(io, mode);
 }
-template <int K, int M, int MODE, bool PLN = false>
-__device__ __forceinline__ void mont_call(const WarpIO<K, M, PLN>& io) {
-  mont_call_rt<K, M, PLN>(io, MODE);
+template <int K, int M, int MODE, bool PLN = false, bool SCHED = false>
+__device__ __forceinline__ void mont_call(const WarpIO<K, M, PLN, SCHED>& io) {
+  mont_call_rt<K, M, PLN, SCHED>(io, MODE);
+}
+// all threads of the CTA fill the schedule table (sched_offset<M>(kSchedModes) words at `tab`)
+template <int M>
+__device__ __forceinline__ void fill_schedule(uint32_t* tab) {
+  const int n = sched_offset<M>(kSchedModes);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = sched_entry<M>(i);
 }
 
 template <int K, int M>

@@ -10,6 +10,23 @@
 
 namespace dkg {
 
+// Words of the tabulated pair schedule (all five modes of the Montgomery product, each list with a
+// terminator; dkg_mont.cuh "tabulated schedule") for M blocks: the host sizes the kernel's shared
+// memory with it, the kernel static_asserts that it equals what ColPlan generates.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int sched_total_words_closed(int M) {
+  int half = 0;  // sum over columns of ceil(span / 2): the operand pairs of a squaring
+  for (int c = 0; c < 2 * M; ++c) {
+    const int lo = c >= M ? c - M + 1 : 0, hi = c < M ? c : M - 1, span = hi - lo + 1;
+    half += span / 2 + (span & 1);
+  }
+  const int mm = M * M;
+  // MUL 2M^2, REDC M^2, SQR half + M^2, MUL2S 2M^2, MULADD 3M^2, plus five terminators
+  return 2 * mm + mm + (half + mm) + 2 * mm + 3 * mm + 5;
+}
+
 struct ModexpParams {
   const uint32_t* bases;   // [count][in_limbs]
   uint32_t* out;           // [count][in_limbs]

@@ -234,8 +234,8 @@ DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32
 // Pair schedule of column c of the block product scan.
 template <int M>
 struct ColPlan {
-  int lo, span, nxy, ndouble, nq, total, MODE;
-  DKG_HD ColPlan(int c, int mode) {
+  int lo = 0, span = 0, nxy = 0, ndouble = 0, nq = 0, total = 0, MODE = 0;
+  DKG_HD constexpr ColPlan(int c, int mode) {
     MODE = mode;
     lo = c >= M ? c - M + 1 : 0;
     const int hi = c < M ? c : M - 1;
@@ -250,9 +250,8 @@ struct ColPlan {
   // squaring / doubled product: operand products (the leading `ndouble` are doubled), N*Q
   //   products, quotient step
   // multiplication / multiply-add / reduction: N*Q products, operand products, quotient step
-  DKG_HD PairDesc at(int c, int t) const {
-    PairDesc d;
-    d.xi = 0; d.yi = 0;
+  DKG_HD constexpr PairDesc at(int c, int t) const {
+    PairDesc d{PAIR_NONE, 0, 0};
     if (MODE == MONT_SQR || MODE == MONT_MUL2S) {
       if (t < nxy) { d.kind = (MODE == MONT_SQR) ? PAIR_XX : PAIR_XS; d.xi = lo + t; d.yi = c - d.xi; }
       else if (t < nxy + nq) { d.kind = PAIR_NQ; d.yi = lo + (t - nxy); d.xi = c - d.yi; }
@@ -268,6 +267,50 @@ struct ColPlan {
     return d;
   }
 };
+
+// ---- tabulated schedule -------------------------------------------------------------------------
+// The pair sequence of one Montgomery product depends only on (M, mode).  Computing "what comes
+// next" from ColPlan inside the block-product loop costs ~70 uniform-datapath instructions and 9
+// branches per block product; an IO policy with SCHED = true instead reads it from a table
+// (one word per pair, all pairs of a mode in execution order, then a PAIR_NONE terminator) that the
+// kernel fills once at start with the very same ColPlan.
+DKG_HD uint32_t pack_desc(const PairDesc& d) { return (uint32_t)d.kind | ((uint32_t)d.xi << 8) | ((uint32_t)d.yi << 16); }
+DKG_HD PairDesc unpack_desc(uint32_t w) {
+  PairDesc d;
+  d.kind = (int)(w & 0xffu); d.xi = (int)((w >> 8) & 0xffu); d.yi = (int)((w >> 16) & 0xffu);
+  return d;
+}
+constexpr int kSchedModes = 5;
+// words of mode `mode`'s list (pairs + terminator) / offset of its first word
+template <int M>
+DKG_HD constexpr int sched_words(int mode) {
+  int n = 1;
+  for (int c = 0; c < 2 * M; ++c) n += ColPlan<M>(c, mode).total;
+  return n;
+}
+template <int M>
+DKG_HD constexpr int sched_offset(int mode) {
+  int off = 0;
+  for (int m = 0; m < mode; ++m) off += sched_words<M>(m);
+  return off;
+}
+// entry `i` of the whole table (all modes back to back), for the fill loop
+template <int M>
+DKG_HD uint32_t sched_entry(int i) {
+  for (int mode = 0; mode < kSchedModes; ++mode) {
+    const int n = sched_words<M>(mode);
+    if (i >= n) { i -= n; continue; }
+    for (int c = 0; c < 2 * M; ++c) {
+      const ColPlan<M> plan(c, mode);
+      if (i < plan.total) return pack_desc(plan.at(c, i));
+      i -= plan.total;
+    }
+    break;
+  }
+  PairDesc none;
+  none.kind = PAIR_NONE; none.xi = 0; none.yi = 0;
+  return pack_desc(none);
+}
 
 // IO policy (all indices are block indices; r has K limbs; VW = limbs per vector):
 //   load_x(i, r)  load_s(i, r)  load_y(j, r)  load_q(i, r)  load_n(j, r)  load_ninv(r)
@@ -290,6 +333,9 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
 #pragma unroll
   for (int i = 0; i < K + 2; i++) Tc[i] = 0;
   acc_clear_side<K>(a);
+
+  // position of the NEXT pair in the tabulated schedule (SCHED IO policies)
+  auto sched = io.sched_begin(IO::SCHED ? sched_offset<M>(MODE) + 1 : 0);
 
   uint32_t xb[K], yb[K];
   // operands of the very first block product (everything after it is prefetched)
@@ -371,16 +417,20 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
         // what comes next (possibly in the next column): its y operand is prefetched behind this
         // block product, its x operand loaded right after
         PairDesc nx;
-        nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
-        if (t + 1 < plan.total) nx = plan.at(c, t + 1);
-        else if (c + 1 < 2 * M) {
-          const Plan np(c + 1, MODE);
-          if (np.total > 0) nx = np.at(c + 1, 0);
+        if constexpr (IO::SCHED) {
+          nx = unpack_desc(io.sched_word(sched, 0));
+          sched = io.sched_next(sched);
+        } else {
+          nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
+          if (t + 1 < plan.total) nx = plan.at(c, t + 1);
+          else if (c + 1 < 2 * M) {
+            const Plan np(c + 1, MODE);   // only the very last column can be empty
+            if (np.total > 0) nx = np.at(c + 1, 0);
+          }
         }
         block_mac<K>(a, xb, yb, io, io.prefetch_desc(nx.kind, nx.yi));
-        if (nx.kind == PAIR_XY || nx.kind == PAIR_XX || nx.kind == PAIR_XS) io.load_x(nx.xi, xb);
-        else if (nx.kind == PAIR_SY2) io.load_s(nx.xi, xb);
-        else if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
+        if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
+        else if (nx.kind != PAIR_QC && nx.kind != PAIR_NONE) io.load_xs(nx.kind == PAIR_SY2, nx.xi, xb);
       }
     }
     if (plan.total > 0) acc_merge<K>(a, e);

@@ -83,8 +83,12 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const type
   }
 }
 
+template <int M>
+constexpr int kNsqSchedWords = sched_offset<M>(kSchedModes);
+
 template <int K, int M>
 __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const NsqParams p) {
+  static_assert(kNsqSchedWords<M> == sched_total_words_closed(M), "schedule table size: host formula out of sync with ColPlan");
   using V = typename VecSel<K>::T;
   constexpr int VW = VecSel<K>::VW;
   constexpr int Lp = K * M;
@@ -92,9 +96,12 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // N[Lp] | NINV[K] | DNEG[Lp]
-  constexpr int UNI = ((2 * Lp + K) * 4 + 15) / 16 * 16;
+  constexpr int UNI0 = ((2 * Lp + K) * 4 + 15) / 16 * 16;
+  // ... | schedule table (kNsqSchedWords<M> words, see fill_schedule)
+  constexpr int UNI = UNI0 + (kNsqSchedWords<M> * 4 + 15) / 16 * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * Lp + K; i += blockDim.x) U32[i] = p.consts[i];
+  fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw + UNI0));
   __syncthreads();
   const uint32_t* Ns32 = U32;
   const uint32_t* Dneg = U32 + Lp + K;
@@ -117,7 +124,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
 
   const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(Aw + lane);
   const uint32_t b_s = (uint32_t)__cvta_generic_to_shared(Bw + lane);
-  WarpIO<K, M> io;
+  WarpIO<K, M, false, true> io;
+  io.sched_s = (uint32_t)__cvta_generic_to_shared(smem_raw + UNI0);
   io.ns = (uint32_t)__cvta_generic_to_shared(Ns32);
   io.nis = (uint32_t)__cvta_generic_to_shared(Ns32 + Lp);
   io.Qg = Qg + lane;
@@ -125,16 +133,16 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   // (A, B) <- (A, B) * (c, d): c, d in global memory, lane layout
   auto pair_mul = [&](const V* c, const V* d) {
     io.xs = b_s; io.ss = a_s; io.Y = c; io.Y2 = d;
-    mont_call<K, M, MONT_MULADD>(io);                 // B <- REDC(B c + A d)
+    mont_call<K, M, MONT_MULADD, false, true>(io);                 // B <- REDC(B c + A d)
     io.xs = a_s;
-    mont_call<K, M, MONT_MUL>(io);                    // A <- REDC(A c), quotient m in Q
+    mont_call<K, M, MONT_MUL, false, true>(io);                    // A <- REDC(A c), quotient m in Q
     pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
   };
   auto pair_sqr = [&]() {
     io.xs = b_s; io.ss = a_s;
-    mont_call<K, M, MONT_MUL2S>(io);                  // B <- REDC(2 B A)
+    mont_call<K, M, MONT_MUL2S, false, true>(io);                  // B <- REDC(2 B A)
     io.xs = a_s;
-    mont_call<K, M, MONT_SQR>(io);                    // A <- REDC(A^2), quotient m in Q
+    mont_call<K, M, MONT_SQR, false, true>(io);                    // A <- REDC(A^2), quotient m in Q
     pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
   };
 

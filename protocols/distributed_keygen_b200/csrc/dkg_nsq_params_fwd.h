@@ -1,6 +1,7 @@
 // Launch parameters of the pair-arithmetic (modulus N^2) exponentiation kernel.
 #pragma once
 #include <stdint.h>
+#include "dkg_modexp_params.h"
 
 namespace dkg {
 

@@ -11,8 +11,13 @@ struct HostIO {
   uint32_t* X; const uint32_t* Y; uint32_t* Q; const uint32_t* N; const uint32_t* NI;
   const uint32_t* S = nullptr; const uint32_t* Y2 = nullptr;
   bool never() const { return false; }
+  static constexpr bool SCHED = false;   // the host harness recomputes the schedule from ColPlan
+  int sched_begin(int) const { return 0; }
+  int sched_next(int p) const { return p; }
+  uint32_t sched_word(int, int) const { return 0; }
   void load_s(int i, uint32_t (&r)[K]) const { std::memcpy(r, S + i * K, K * 4); }
   void load_x(int i, uint32_t (&r)[K]) const { std::memcpy(r, X + i * K, K * 4); }
+  void load_xs(bool from_s, int i, uint32_t (&r)[K]) const { std::memcpy(r, (from_s ? S : X) + i * K, K * 4); }
   void load_y(int j, uint32_t (&r)[K]) const { std::memcpy(r, Y + j * K, K * 4); }
   void load_q(int i, uint32_t (&r)[K]) const { std::memcpy(r, Q + i * K, K * 4); }
   void load_n(int j, uint32_t (&r)[K]) const { std::memcpy(r, N + j * K, K * 4); }
