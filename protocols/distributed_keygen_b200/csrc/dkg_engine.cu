@@ -282,6 +282,18 @@ std::vector<uint32_t> sliding_window_ops(const uint32_t* e, int ebits, int w, in
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
                       size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows = nullptr, int m_limbs = 0);
 
+// Chain warps of the batched inversion: chains of 32 groups keep the binary-GCD count at 1/32 of
+// the elements but leave most SMs idle (56 warps for a 56 832-element launch); the chain products
+// dominate, so spread them over every SM as long as a chain keeps at least 4 groups.
+int inversion_chain_warps(const DeviceState* d, const dkg_modexp_ctx* ctx, unsigned long long ngroups);
+
+int inversion_chain_warps(const DeviceState* d, const dkg_modexp_ctx* ctx, unsigned long long ngroups) {
+  unsigned long long nchain = (ngroups + 31) / 32;
+  const unsigned long long wide = std::min<unsigned long long>((unsigned long long)d->sm_count * std::max(ctx->inv_warps, 1), ngroups / 4);
+  if (wide > nchain) nchain = wide;
+  return (int)std::max<unsigned long long>(nchain, 1);
+}
+
 int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
                   const uint32_t* d_final_mul, size_t count, cudaStream_t stream) {
   if (count == 0) return DKG_OK;
@@ -303,7 +315,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
   if (ctx->negative && ctx->inv_kernel != nullptr && ngroups >= 2 && !getenv("DKG_NO_BATCH_INVERSE")) {
     // Montgomery's trick along chains of ~32 groups: one binary-GCD inversion per chain lane
     const size_t gwords = (size_t)ctx->Lp * 32;
-    const int nchain = (int)((ngroups + 31) / 32);
+    const int nchain = inversion_chain_warps(d, ctx, ngroups);
     const int chain_len = (int)((ngroups + nchain - 1) / nchain);
     const size_t words = 2 * ngroups * gwords + (size_t)nchain * gwords + (size_t)nchain * 32;
     rc = ensure_aux(d, words);
@@ -344,7 +356,7 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   if (ctx->negative) {
     if (ctx->inv_kernel == nullptr || ngroups < 1) return DKG_OK;  // let the direct kernel do it
     const size_t gwords = (size_t)ctx->Lp * 32;
-    const int nchain = (int)((ngroups + 31) / 32);
+    const int nchain = inversion_chain_warps(d, ctx, ngroups);
     const int chain_len = (int)((ngroups + nchain - 1) / nchain);
     inv_words = 2 * ngroups * gwords + (size_t)nchain * gwords + (size_t)nchain * 32 + 32 + count * (size_t)ctx->limbs;
     int rc = ensure_aux(d, inv_words + pair_words);
