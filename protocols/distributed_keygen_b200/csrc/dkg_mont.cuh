@@ -133,9 +133,9 @@ template <int K>
 DKG_HD void acc_merge(ColAcc<K>& a, uint32_t (&e)[2 * K + 2]) {
   uint32_t o[2 * K - 2];
 #pragma unroll
-  for (int p = 0; p < K + 1; p++) { e[2 * p] = (uint32_t)a.E[p]; e[2 * p + 1] = (uint32_t)(a.E[p] >> 32); }
+  for (int p = 0; p < K + 1; p++) unpack64(a.E[p], e[2 * p], e[2 * p + 1]);
 #pragma unroll
-  for (int p = 0; p < K - 1; p++) { o[2 * p] = (uint32_t)a.O[p]; o[2 * p + 1] = (uint32_t)(a.O[p] >> 32); }
+  for (int p = 0; p < K - 1; p++) unpack64(a.O[p], o[2 * p], o[2 * p + 1]);
   add_cc(e[1], o[0]);
 #pragma unroll
   for (int p = 1; p < 2 * K - 2; p++) addc_cc(e[p + 1], o[p]);
@@ -187,7 +187,7 @@ DKG_HD void acc_low(const ColAcc<K>& a, uint32_t (&tl)[K]) {
 template <int K>
 DKG_HD void acc_load(ColAcc<K>& a, const uint32_t (&e)[2 * K + 2]) {
 #pragma unroll
-  for (int p = 0; p < K + 1; p++) a.E[p] = ((uint64_t)e[2 * p + 1] << 32) | e[2 * p];
+  for (int p = 0; p < K + 1; p++) a.E[p] = pack64(e[2 * p], e[2 * p + 1]);
 }
 
 // r = x[0..K) * y mod 2^(32K)   (x is the low block of a wider array)

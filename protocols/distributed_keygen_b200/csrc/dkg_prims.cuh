@@ -43,6 +43,17 @@ DKG_HD void madc_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
   asm volatile("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmadc.lo.cc.u32 l, %1, %2, l;\n\t"
                "madc.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
 }
+// Explicit pair <-> halves moves.  Written as (volatile) mov.b64 rather than shifts and ors: ptxas
+// then keeps the halves where the pair lives; with the C++ form it re-paired ~30 more registers
+// per block product.
+DKG_HD uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t v;
+  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+  return v;
+}
+DKG_HD void unpack64(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
 // lo += lo32(a*b)                     (no flags)
 DKG_HD void mad_lo(uint32_t& lo, uint32_t a, uint32_t b) {
   asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
@@ -89,6 +100,8 @@ DKG_HD void madc_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
   madc_cc(lo, hi, a, b);
   acc = ((uint64_t)hi << 32) | lo;
 }
+DKG_HD uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+DKG_HD void unpack64(uint64_t v, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
 DKG_HD void mad_lo(uint32_t& lo, uint32_t a, uint32_t b) { lo += a * b; }
 DKG_HD void madc_lo(uint32_t& lo, uint32_t a, uint32_t b) { lo += a * b + detail::cf(); }
 DKG_HD void add_cc(uint32_t& x, uint32_t y) { detail::add3(x, y, 0, true); }
