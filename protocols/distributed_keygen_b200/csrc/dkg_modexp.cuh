@@ -121,6 +121,27 @@ struct WarpIO {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, base + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
+  // limb l of X
+  __device__ __forceinline__ uint32_t x_limb(int l) const {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xs + (uint32_t)(l / VW) * 32u * VB + (uint32_t)(l % VW) * 4u));
+    return w;
+  }
+  // block i of 2*S (from_s) or 2*X: every limb shifted left by one, the bit shifted in is the top
+  // bit of the limb below (of block i-1 for the first limb)
+  __device__ __forceinline__ void load_xs2(bool from_s, int i, uint32_t (&r)[K]) const {
+    const uint32_t base = from_s ? ss : xs;
+    uint32_t prev = 0;
+    if (i > 0) {
+      const int l = i * K - 1;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(prev) : "r"(base + (uint32_t)(l / VW) * 32u * VB + (uint32_t)(l % VW) * 4u));
+    }
+#pragma unroll
+    for (int q = 0; q < KV; q++) { V v; lds_vec(v, base + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
+#pragma unroll
+    for (int p = K - 1; p > 0; p--) r[p] = __funnelshift_l(r[p - 1], r[p], 1);
+    r[0] = __funnelshift_l(prev, r[0], 1);
+  }
   __device__ __forceinline__ void load_y(int j, uint32_t (&r)[K]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Y + (size_t)(j * KV + q) * 32); unpack(v, &r[q * VW]); }
@@ -135,7 +156,7 @@ struct WarpIO {
   struct Prefetch { const char* gbase; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
-    d.on_s = (kind == PAIR_XX || kind == PAIR_XS) ? 1u : 0u;
+    d.on_s = (kind == PAIR_XX || kind == PAIR_XS || kind == PAIR_XX2 || kind == PAIR_SX2) ? 1u : 0u;
     d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
     d.sbase = (kind == PAIR_XS ? ss : xs) + (uint32_t)(blk * KV) * 32u * VB;
     const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : Qg);

@@ -35,9 +35,6 @@ enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2, MONT_MUL2S = 3, MONT_
 // its cycles, profiles/r01_ncu_nsq_source_opcodes.txt).  A block of FFMAs that is never executed
 // (guarded by io.never(), a run-time condition that is never true) tips the static balance, and every one of those instructions
 // moves to the idle ALU pipe.  It costs code bytes that are never fetched.
-#ifndef DKG_INPLACE_DOUBLE
-#define DKG_INPLACE_DOUBLE 0
-#endif
 #ifndef DKG_PIPE_BALLAST
 #define DKG_PIPE_BALLAST 3072
 #endif
@@ -85,7 +82,12 @@ DKG_HD void acc_clear_side(ColAcc<K>& a) {
 //   PAIR_QC: the quotient step (x = Q_c fresh in registers, y = N_0)
 //   PAIR_XS: x = X_i, y = S_j (second shared-memory operand)
 //   PAIR_SY2: x = S_i, y = Y2_j (second global operand)
-enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4, PAIR_XS = 5, PAIR_SY2 = 6 };
+//   PAIR_XX2: x = block i of 2*X, y = X_j (cross product of a squaring, i < j)
+//   PAIR_SX2: x = block i of 2*S, y = X_j (doubled product)
+// "block i of 2*V" = (V_i << 1 | top bit of V_{i-1}) mod 2^(32K): the factor 2 of the squaring
+// modes is applied to an operand as it is loaded, not to the accumulated products.
+enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4, PAIR_XS = 5, PAIR_SY2 = 6,
+                PAIR_XX2 = 7, PAIR_SX2 = 8 };
 
 struct PairDesc {
   int kind, xi, yi;
@@ -153,34 +155,18 @@ DKG_HD void acc_merge(ColAcc<K>& a, uint32_t (&e)[2 * K + 2]) {
   acc_clear_side<K>(a);
 }
 
-// a <- 2*a + bit, component by component (the carry-save form is linear): no merge, no carry
-// chain, every shift independent of the others.  The bit leaving the top of O has the weight of
-// the last CO counter; E has two limbs of headroom.
-template <int K>
-DKG_HD void acc_double(ColAcc<K>& a, uint32_t bit) {
-#pragma unroll
-  for (int k = 0; k < K / 2 + 1; k++) a.CE[k] <<= 1;
-#pragma unroll
-  for (int k = 0; k < K / 2; k++) a.CO[k] <<= 1;
-  a.CO[K / 2 - 1] += (uint32_t)(a.O[K - 2] >> 63);
-#pragma unroll
-  for (int p = K - 2; p > 0; p--) a.O[p] = (a.O[p] << 1) | (a.O[p - 1] >> 63);
-  a.O[0] <<= 1;
-#pragma unroll
-  for (int p = K; p > 0; p--) a.E[p] = (a.E[p] << 1) | (a.E[p - 1] >> 63);
-  a.E[0] = (a.E[0] << 1) | bit;
-}
-
 // low block of the accumulated value: (E + (O << 32)) mod 2^(32K); a is not modified
 template <int K>
 DKG_HD void acc_low(const ColAcc<K>& a, uint32_t (&tl)[K]) {
 #pragma unroll
-  for (int p = 0; p < K / 2; p++) { tl[2 * p] = (uint32_t)a.E[p]; tl[2 * p + 1] = (uint32_t)(a.E[p] >> 32); }
-  add_cc(tl[1], (uint32_t)a.O[0]);
+  for (int p = 0; p < K / 2; p++) unpack64(a.E[p], tl[2 * p], tl[2 * p + 1]);
+  uint32_t o[K];  // O limbs 0..K-1 (O limb q sits at limb position q+1)
+#pragma unroll
+  for (int p = 0; p < K / 2; p++) unpack64(a.O[p], o[2 * p], o[2 * p + 1]);
+  add_cc(tl[1], o[0]);
 #pragma unroll
   for (int p = 2; p < K; p++) {
-    const uint32_t o = (p & 1) ? (uint32_t)a.O[(p - 1) / 2] : (uint32_t)(a.O[(p - 2) / 2] >> 32);
-    if (p < K - 1) addc_cc(tl[p], o); else addc(tl[p], o);
+    if (p < K - 1) addc_cc(tl[p], o[p - 1]); else addc(tl[p], o[p - 1]);
   }
 }
 
@@ -231,39 +217,42 @@ DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32
   addc(r[K - 1], O[K - 2]);
 }
 
-// Pair schedule of column c of the block product scan.
+// Pair schedule of column c of the block product scan: N*Q products, operand products, quotient
+// step, in that order for every mode.
+//
+// Squaring: sum_{i<j} 2 X_i X_j W^(i+j) (W = 2^(32K)) is formed with the doubled operand,
+//   sum_{i<j} D_i X_j W^(i+j) + sum_{j>=1} t_{j-1} X_j W^(2j),   D = blocks of 2X mod W^M,
+// where t_{j-1} is the top bit of block j-1: doubling the low j blocks of X carries that bit out
+// to block position j, and the triangular sum has no pair (j, j) to absorb it.  The second sum is
+// the "carry-bit correction" mont_mul adds at the start of column 2j.  The top block is never
+// doubled (i <= M-2), so this holds for every X < R.
+// Doubled product (MUL2S): 2*X*S = X * (2S) block by block; rectangular, no correction, but 2S must
+// fit: S < R/2 (the pair arithmetic's a < 2N <= R/4).
 template <int M>
 struct ColPlan {
-  int lo = 0, span = 0, nxy = 0, ndouble = 0, nq = 0, total = 0, MODE = 0;
+  int lo = 0, span = 0, nxy = 0, nq = 0, total = 0, MODE = 0;
   DKG_HD constexpr ColPlan(int c, int mode) {
     MODE = mode;
     lo = c >= M ? c - M + 1 : 0;
     const int hi = c < M ? c : M - 1;
     span = hi - lo + 1;                               // X_i * Y_{c-i}, i in [lo, hi]
-    // squaring: pairs i < c-i once (doubled afterwards), the middle i == c-i once more
-    ndouble = (MODE == MONT_SQR) ? span / 2 : (MODE == MONT_MUL2S ? span : 0);
+    // squaring: pairs i < c-i (doubled operand) and the middle i == c-i
     nxy = (MODE == MONT_MUL || MODE == MONT_MUL2S) ? span
           : (MODE == MONT_SQR ? span / 2 + (span & 1) : (MODE == MONT_MULADD ? 2 * span : 0));
     nq = (c < M ? c - 1 : M - 1) - lo + 1;            // Q_i * N_{c-i}, i in [lo, ..]
     total = nxy + nq + (c < M ? 1 : 0);               // + the quotient step
   }
-  // squaring / doubled product: operand products (the leading `ndouble` are doubled), N*Q
-  //   products, quotient step
-  // multiplication / multiply-add / reduction: N*Q products, operand products, quotient step
   DKG_HD constexpr PairDesc at(int c, int t) const {
     PairDesc d{PAIR_NONE, 0, 0};
-    if (MODE == MONT_SQR || MODE == MONT_MUL2S) {
-      if (t < nxy) { d.kind = (MODE == MONT_SQR) ? PAIR_XX : PAIR_XS; d.xi = lo + t; d.yi = c - d.xi; }
-      else if (t < nxy + nq) { d.kind = PAIR_NQ; d.yi = lo + (t - nxy); d.xi = c - d.yi; }
-      else d.kind = PAIR_QC;
-    } else {
-      if (t < nq) { d.kind = PAIR_NQ; d.yi = lo + t; d.xi = c - d.yi; }
-      else if (t < nq + nxy) {
-        const int u = t - nq;
-        if (MODE == MONT_MULADD && u >= span) { d.kind = PAIR_SY2; d.xi = lo + (u - span); d.yi = c - d.xi; }
-        else { d.kind = PAIR_XY; d.xi = lo + u; d.yi = c - d.xi; }
-      } else d.kind = PAIR_QC;
-    }
+    if (t < nq) { d.kind = PAIR_NQ; d.yi = lo + t; d.xi = c - d.yi; }
+    else if (t < nq + nxy) {
+      const int u = t - nq;
+      if (MODE == MONT_MULADD && u >= span) { d.kind = PAIR_SY2; d.xi = lo + (u - span); d.yi = c - d.xi; }
+      else {
+        d.xi = lo + u; d.yi = c - d.xi;
+        d.kind = MODE == MONT_SQR ? (d.xi < d.yi ? PAIR_XX2 : PAIR_XX) : (MODE == MONT_MUL2S ? PAIR_SX2 : PAIR_XY);
+      }
+    } else d.kind = PAIR_QC;
     return d;
   }
 };
@@ -343,26 +332,15 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
     const PairDesc d = Plan(0, MODE).at(0, 0);
     if (d.kind == PAIR_XY) { io.load_x(d.xi, xb); io.load_y(d.yi, yb); }
     else if (d.kind == PAIR_XX) { io.load_x(d.xi, xb); io.load_x(d.yi, yb); }
-    else if (d.kind == PAIR_XS) { io.load_x(d.xi, xb); io.load_s(d.yi, yb); }
+    else if (d.kind == PAIR_SX2) { io.load_xs2(true, d.xi, xb); io.load_x(d.yi, yb); }
   }
 
   for (int c = 0; c < 2 * M; ++c) {
     const Plan plan(c, MODE);
-    const bool defer_carry = plan.ndouble > 0;
 
-    // Seed the accumulator with the carry-in.  Where the leading products get doubled, seed with
-    // HALF the carry-in and keep its low bit aside: 2*(Tc >> 1) + (Tc & 1) = Tc after the doubling,
-    // so the K+2 carry-in limbs need not stay in registers across those block products.
-    uint32_t tc_bit = 0;
-    if (!defer_carry) {
+    // seed the accumulator with the carry-in
 #pragma unroll
-      for (int p = 0; p < K + 2; p++) e[p] = Tc[p];
-    } else {
-      tc_bit = Tc[0] & 1u;
-#pragma unroll
-      for (int p = 0; p < K + 1; p++) e[p] = (Tc[p] >> 1) | (Tc[p + 1] << 31);
-      e[K + 1] = Tc[K + 1] >> 1;
-    }
+    for (int p = 0; p < K + 2; p++) e[p] = Tc[p];
 #pragma unroll
     for (int p = K + 2; p < 2 * K + 2; p++) e[p] = 0;
 
@@ -376,29 +354,27 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
       for (int p = K; p <= 2 * K; p++) addc_cc(e[p], 0);
       addc(e[2 * K + 1], 0);
     }
-    // The column's block products run in up to three stretches separated by two events: the
-    // doubling of the cross products (squaring modes; done in place on the carry-save form) and the
-    // quotient step (which needs the merged low block).  All stretches run the SAME inner loop,
-    // whose body is nothing but the block product and its operand traffic; the accumulator enters
-    // it from the 32-bit view e through the SAME acc_load (column start and quotient step).
-    const int t_double = ((MODE == MONT_SQR || MODE == MONT_MUL2S) && defer_carry) ? plan.ndouble : -1;
+    if (MODE == MONT_SQR && (c & 1) == 0 && c >= 2) {
+      // carry-bit correction of the doubled operand (see ColPlan): + t_{j-1} * X_j at column 2j
+      const int j = c >> 1;
+      const uint32_t mask = 0u - (io.x_limb(j * K - 1) >> 31);
+      uint32_t tb[K];
+      io.load_x(j, tb);
+      add_cc(e[0], tb[0] & mask);
+#pragma unroll
+      for (int p = 1; p < K; p++) addc_cc(e[p], tb[p] & mask);
+#pragma unroll
+      for (int p = K; p <= 2 * K; p++) addc_cc(e[p], 0);
+      addc(e[2 * K + 1], 0);
+    }
+    // The column's block products run in two stretches around the quotient step, through the SAME
+    // inner loop, whose body is nothing but the block product and its operand traffic; the
+    // accumulator enters it once per column from the 32-bit view e (acc_load) and is folded back
+    // once (acc_merge) -- the quotient step only reads its low block.
     const int t_quot = c < M ? plan.total - 1 : -1;
     int t = 0;
     while (t < plan.total) {
-#if DKG_INPLACE_DOUBLE
-      // all products that count twice are in (plus half the carry-in): double, in place
-      if (t == t_double) acc_double<K>(a, tc_bit);
       if (t == 0) acc_load<K>(a, e);
-#else
-      if (t == t_double) {
-        // all products that count twice are in (plus half the carry-in): double
-        acc_merge<K>(a, e);
-#pragma unroll
-        for (int p = 2 * K + 1; p > 0; p--) e[p] = (e[p] << 1) | (e[p - 1] >> 31);
-        e[0] = (e[0] << 1) | tc_bit;
-      }
-      if (t == 0 || t == t_double) acc_load<K>(a, e);
-#endif
       if (t == t_quot) {
         // quotient block: Q_c = T_low * (-N^-1) mod 2^(32K); Q_c * N_0 then clears T_low.  T_low
         // needs only the low blocks of E and O (the counters weigh 2^(32K) and more), so the
@@ -411,8 +387,7 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
         io.load_n(0, yb);
       }
       int t_end = plan.total;
-      if (t < t_double) t_end = t_double;
-      else if (t < t_quot) t_end = t_quot;
+      if (t < t_quot) t_end = t_quot;
       for (; t < t_end; ++t) {
         // what comes next (possibly in the next column): its y operand is prefetched behind this
         // block product, its x operand loaded right after
@@ -430,6 +405,7 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
         }
         block_mac<K>(a, xb, yb, io, io.prefetch_desc(nx.kind, nx.yi));
         if (nx.kind == PAIR_NQ) io.load_n(nx.xi, xb);
+        else if (nx.kind == PAIR_XX2 || nx.kind == PAIR_SX2) io.load_xs2(nx.kind == PAIR_SX2, nx.xi, xb);
         else if (nx.kind != PAIR_QC && nx.kind != PAIR_NONE) io.load_xs(nx.kind == PAIR_SY2, nx.xi, xb);
       }
     }

@@ -17,6 +17,14 @@ struct HostIO {
   uint32_t sched_word(int, int) const { return 0; }
   void load_s(int i, uint32_t (&r)[K]) const { std::memcpy(r, S + i * K, K * 4); }
   void load_x(int i, uint32_t (&r)[K]) const { std::memcpy(r, X + i * K, K * 4); }
+  uint32_t x_limb(int l) const { return X[l]; }
+  void load_xs2(bool from_s, int i, uint32_t (&r)[K]) const {
+    const uint32_t* v = from_s ? S : X;
+    for (int p = 0; p < K; ++p) {
+      const int l = i * K + p;
+      r[p] = (v[l] << 1) | (l > 0 ? v[l - 1] >> 31 : 0u);
+    }
+  }
   void load_xs(bool from_s, int i, uint32_t (&r)[K]) const { std::memcpy(r, (from_s ? S : X) + i * K, K * 4); }
   void load_y(int j, uint32_t (&r)[K]) const { std::memcpy(r, Y + j * K, K * 4); }
   void load_q(int i, uint32_t (&r)[K]) const { std::memcpy(r, Q + i * K, K * 4); }
@@ -26,7 +34,7 @@ struct HostIO {
   struct Prefetch { const uint32_t* base; };
   Prefetch prefetch_desc(int kind, int blk) const {
     if (kind == dkg::PAIR_XY) return Prefetch{Y + blk * K};
-    if (kind == dkg::PAIR_XX) return Prefetch{X + blk * K};
+    if (kind == dkg::PAIR_XX || kind == dkg::PAIR_XX2 || kind == dkg::PAIR_SX2) return Prefetch{X + blk * K};
     if (kind == dkg::PAIR_NQ) return Prefetch{Q + blk * K};
     if (kind == dkg::PAIR_XS) return Prefetch{S + blk * K};
     if (kind == dkg::PAIR_SY2) return Prefetch{Y2 + blk * K};
