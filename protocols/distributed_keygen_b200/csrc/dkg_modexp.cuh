@@ -156,9 +156,9 @@ struct WarpIO {
   struct Prefetch { const char* gbase; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
-    d.on_s = (kind == PAIR_XX || kind == PAIR_XS || kind == PAIR_XX2 || kind == PAIR_SX2) ? 1u : 0u;
+    d.on_s = (kind == PAIR_XX || kind == PAIR_XX2 || kind == PAIR_SX2) ? 1u : 0u;
     d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
-    d.sbase = (kind == PAIR_XS ? ss : xs) + (uint32_t)(blk * KV) * 32u * VB;
+    d.sbase = xs + (uint32_t)(blk * KV) * 32u * VB;
     const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : Qg);
     d.gbase = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
     return d;

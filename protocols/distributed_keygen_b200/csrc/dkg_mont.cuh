@@ -80,13 +80,12 @@ DKG_HD void acc_clear_side(ColAcc<K>& a) {
 //   PAIR_XX: x = X_i, y = X_j (shared; squaring)
 //   PAIR_NQ: x = N_i (shared, CTA-uniform), y = Q_j (global scratch, written earlier by this thread)
 //   PAIR_QC: the quotient step (x = Q_c fresh in registers, y = N_0)
-//   PAIR_XS: x = X_i, y = S_j (second shared-memory operand)
 //   PAIR_SY2: x = S_i, y = Y2_j (second global operand)
 //   PAIR_XX2: x = block i of 2*X, y = X_j (cross product of a squaring, i < j)
 //   PAIR_SX2: x = block i of 2*S, y = X_j (doubled product)
 // "block i of 2*V" = (V_i << 1 | top bit of V_{i-1}) mod 2^(32K): the factor 2 of the squaring
 // modes is applied to an operand as it is loaded, not to the accumulated products.
-enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4, PAIR_XS = 5, PAIR_SY2 = 6,
+enum PairKind { PAIR_XY = 0, PAIR_XX = 1, PAIR_NQ = 2, PAIR_QC = 3, PAIR_NONE = 4, PAIR_SY2 = 6,
                 PAIR_XX2 = 7, PAIR_SX2 = 8 };
 
 struct PairDesc {
@@ -302,7 +301,7 @@ DKG_HD uint32_t sched_entry(int i) {
 }
 
 // IO policy (all indices are block indices; r has K limbs; VW = limbs per vector):
-//   load_x(i, r)  load_s(i, r)  load_y(j, r)  load_q(i, r)  load_n(j, r)  load_ninv(r)
+//   load_x(i, r)  load_xs(from_s, i, r)  load_xs2(from_s, i, r)  x_limb(l)  load_y(j, r)  load_n(j, r)  load_ninv(r)
 //   prefetch_desc(kind, block) -> IO::Prefetch ; prefetch_load(desc, v, r)   (vector v of the block)
 //   store_q(i, r) store_x(i, r)
 //

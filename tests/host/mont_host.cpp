@@ -36,7 +36,6 @@ struct HostIO {
     if (kind == dkg::PAIR_XY) return Prefetch{Y + blk * K};
     if (kind == dkg::PAIR_XX || kind == dkg::PAIR_XX2 || kind == dkg::PAIR_SX2) return Prefetch{X + blk * K};
     if (kind == dkg::PAIR_NQ) return Prefetch{Q + blk * K};
-    if (kind == dkg::PAIR_XS) return Prefetch{S + blk * K};
     if (kind == dkg::PAIR_SY2) return Prefetch{Y2 + blk * K};
     return Prefetch{nullptr};
   }
