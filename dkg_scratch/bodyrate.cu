@@ -3,6 +3,71 @@
 #include <vector>
 #include "../protocols/distributed_keygen_b200/csrc/dkg_modexp.cuh"
 using namespace dkg;
+// variant: every row chain split in two (more independent chains, more carry counters)
+template <int K> struct ColAcc2 { uint64_t E[K + 1]; uint64_t O[K - 1]; uint32_t CE[K + 2]; uint32_t CO[K + 2]; };
+template <int K, class IO>
+__device__ __forceinline__ void block_mac_split(ColAcc2<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], const IO& io, const typename IO::Prefetch& pf) {
+  constexpr int VW = IO::VW;
+  constexpr int H = (K / 2) / 2 * 2;   // even split point in units of i (i < H first half)
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const int pe = j & 1;          // parity of i for the E chain
+    // E chain: i = pe, pe+2, ...
+    bool first = true;
+#pragma unroll
+    for (int i = pe; i < K; i += 2) {
+      if (i == pe || i == pe + H) { if (i != pe) addc(a.CE[(i + j) / 2 - 0], 0); mad_cc64(a.E[(i + j) / 2], x[i], y[j]); }
+      else madc_cc64(a.E[(i + j) / 2], x[i], y[j]);
+    }
+    addc(a.CE[(j + K) / 2 + 1], 0);
+    // O chain: i = 1-pe, ...
+#pragma unroll
+    for (int i = 1 - pe; i < K; i += 2) {
+      if (i == 1 - pe || i == 1 - pe + H) { if (i != 1 - pe) addc(a.CO[(i + j - 1) / 2], 0); mad_cc64(a.O[(i + j - 1) / 2], x[i], y[j]); }
+      else madc_cc64(a.O[(i + j - 1) / 2], x[i], y[j]);
+    }
+    addc(a.CO[(j + K) / 2 + 1], 0);
+    if ((j + 1) % VW == 0) io.prefetch_load(pf, (j + 1) / VW - 1, y);
+    (void)first;
+  }
+}
+template <int K, bool PREF>
+__global__ void __launch_bounds__(384, 1) body_kernel_split(uint32_t* out, const uint32_t* in, const int* kinds, int iters) {
+  extern __shared__ uint32_t sm[];
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) sm[i] = in[i];
+  __syncthreads();
+  using IO = WarpIO<K, 5>;
+  IO io;
+  io.xs = (uint32_t)__cvta_generic_to_shared(sm) + (threadIdx.x & 31) * 8;
+  io.ss = io.xs + 4096; io.ns = io.xs + 8192; io.nis = io.ns + 256;
+  io.Qg = (typename IO::V*)(out + 1024) + (threadIdx.x & 31);
+  io.Y = (const typename IO::V*)(in + 8192) + (threadIdx.x & 31);
+  io.Y2 = io.Y + 77;
+  ColAcc2<K> a;
+#pragma unroll
+  for (int i = 0; i < K + 1; i++) a.E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < K - 1; i++) a.O[i] = 0;
+#pragma unroll
+  for (int i = 0; i < K + 2; i++) { a.CE[i] = 0; a.CO[i] = 0; }
+  uint32_t x[K], y[K];
+  io.load_x(0, x); io.load_x(1, y);
+  for (int t = 0; t < iters; ++t) {
+    const int kind = PREF ? kinds[2 * (t & 63)] : PAIR_NONE, blk = kinds[2 * (t & 63) + 1];
+    block_mac_split<K>(a, x, y, io, io.prefetch_desc(kind, blk));
+    if (kind == PAIR_NQ) io.load_n(blk, x);
+    else if (kind != PAIR_NONE) io.load_xs(kind == PAIR_SY2, blk, x);
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < K + 1; i++) s ^= (uint32_t)a.E[i] ^ (uint32_t)(a.E[i] >> 32);
+#pragma unroll
+  for (int i = 0; i < K - 1; i++) s += (uint32_t)a.O[i] ^ (uint32_t)(a.O[i] >> 32);
+#pragma unroll
+  for (int i = 0; i < K + 2; i++) s += a.CE[i] * 3 + a.CO[i];
+  if (iters == -12345) s = pipe_ballast(s, s + 1);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <int K, bool PREF>
 __global__ void __launch_bounds__(384, 1) body_kernel(uint32_t* out, const uint32_t* in, const int* kinds, int iters) {
   extern __shared__ uint32_t sm[];
@@ -24,9 +89,8 @@ __global__ void __launch_bounds__(384, 1) body_kernel(uint32_t* out, const uint3
   for (int t = 0; t < iters; ++t) {
     const int kind = PREF ? kinds[2 * (t & 63)] : PAIR_NONE, blk = kinds[2 * (t & 63) + 1];
     block_mac<K>(a, x, y, io, io.prefetch_desc(kind, blk));
-    if (kind == PAIR_XY || kind == PAIR_XX || kind == PAIR_XS) io.load_x(blk, x);
-    else if (kind == PAIR_SY2) io.load_s(blk, x);
-    else if (kind == PAIR_NQ) io.load_n(blk, x);
+    if (kind == PAIR_NQ) io.load_n(blk, x);
+    else if (kind != PAIR_NONE) io.load_xs(kind == PAIR_SY2, blk, x);
   }
   uint32_t e[2 * K + 2];
   acc_merge<K>(a, e);
@@ -57,5 +121,7 @@ int main() {
   };
   for (int th : {128, 256, 384}) run(body_kernel<14, false>, "no-prefetch", th);
   for (int th : {128, 256, 384}) run(body_kernel<14, true>, "prefetch   ", th);
+  for (int th : {128, 256, 384}) run(body_kernel_split<14, false>, "split nopf ", th);
+  for (int th : {128, 256, 384}) run(body_kernel_split<14, true>, "split pref ", th);
   return 0;
 }
