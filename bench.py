@@ -57,12 +57,14 @@ def canonical_modexp_macs(exp_bits: int, limbs: int) -> float:
 def actual_modexp_macs(info: dict) -> float:
     """Wide multiply-accumulates the kernels really execute per exponentiation (block products of
     K x K limbs, low-half quotient products), from the context's shape and window parameters."""
-    # sliding windows: `windows` multiplications in the main loop (the first one is a table load),
-    # 2^(w-1) - 1 multiplications and one squaring for the table of odd powers, one squaring per
-    # exponent bit below the first window (bounded by the bit length), two domain conversions
+    # `windows` multiplications in the main loop (the first one is a table load), two domain
+    # conversions, one squaring per exponent bit below the first window (bounded by the bit length);
+    # table: 2^w - 2 multiplications (fixed windows, the default), or one squaring and 2^(w-1) - 1
+    # multiplications for the odd powers (DKG_SLIDING_WINDOW=1)
     w, nd = info["window_bits"], info["windows"]
-    n_sqr = max(info["exponent_bits"] - 1, 0) + 1
-    n_mul = max(nd - 1, 0) + ((1 << (w - 1)) - 1) + 2
+    sliding = os.environ.get("DKG_SLIDING_WINDOW", "0") not in ("", "0")
+    n_sqr = max(info["exponent_bits"] - 1, 0) + (1 if sliding else 0)
+    n_mul = max(nd - 1, 0) + (((1 << (w - 1)) - 1) if sliding else ((1 << w) - 2)) + 2
     if info.get("pair_arithmetic"):
         K, M = info["pair_K"], info["pair_M"]
         blk, lo = K * K, K * (K + 1) // 2

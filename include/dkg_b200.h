@@ -74,8 +74,11 @@ int dkg_measure_imad_peak(int device, double* plain_wide_mac_per_s, double* carr
 
 /* ---- fixed modulus, fixed signed exponent (per key) --------------------------------------- */
 /* modulus: odd, mod_limbs limbs (<= DKG_MAX_LIMBS); exponent: magnitude in exp_limbs limbs,
- * sign in exp_negative (0/1).  Precomputes -N^-1, R mod N, R^2 mod N and the sliding-window
- * operation list of the exponent (one list for the whole batch: the exponent belongs to the key). */
+ * sign in exp_negative (0/1).  Precomputes -N^-1, R mod N, R^2 mod N and the operation list of
+ * the exponent (one list for the whole batch: the exponent belongs to the key).  Default: fixed
+ * windows, every window multiplies, so the sequence of operations is independent of the exponent's
+ * bits (only the table index depends on them); environment DKG_SLIDING_WINDOW=1 selects sliding
+ * windows (fewer multiplications, exponent-dependent schedule, as mpz_powm). */
 int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs,
                           const uint32_t* exponent, int exp_limbs, int exp_negative,
                           dkg_modexp_ctx** out);
@@ -86,8 +89,8 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs,
 int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const uint32_t* exponent,
                               int exp_limbs, int exp_negative, dkg_modexp_ctx** out);
 void dkg_modexp_ctx_destroy(dkg_modexp_ctx* ctx);
-/* info[0]=K, [1]=M, [2]=padded limbs, [3]=sliding-window bits w (table of 2^(w-1) odd powers),
- * [4]=windows (multiplications by a table entry in the main loop), [5]=exponent bits,
+/* info[0]=K, [1]=M, [2]=padded limbs, [3]=window bits w, [4]=windows (multiplications in the main
+ * loop), [5]=exponent bits,
  * [6]=warps per CTA, [7]=CTAs, [8]=1 if the pair arithmetic modulo the root is active,
  * [9]=its K, [10]=its M, [11]=its warps per CTA */
 int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[12]);

@@ -193,7 +193,7 @@ struct dkg_modexp_ctx {
   int limbs = 0;  // caller-visible row width
   Shape shape{};
   int Lp = 0;
-  int wbits = 1, nops = 0, tab_entries = 0, nmul = 0, ebits = 0;
+  int wbits = 1, nops = 0, tab_entries = 0, nmul = 0, ebits = 0, table_odd = 0;
   int negative = 0;
   uint32_t n0inv = 0;
   int warps = 1, ctas = 1;
@@ -219,14 +219,14 @@ struct dkg_modexp_ctx {
 
 namespace {
 
-int choose_window(int ebits) {
+int choose_window(int ebits, int max_w = 6) {
   if (const char* f = getenv("DKG_FORCE_WINDOW")) {  // tuning/debug knob
     int w = atoi(f);
-    if (w >= 1 && w <= 6) return w;
+    if (w >= 1 && w <= max_w) return w;
   }
   int best = 1;
   long best_cost = -1;
-  for (int w = 1; w <= 6; ++w) {
+  for (int w = 1; w <= max_w; ++w) {
     long cost = ((1L << w) - 2) + (ebits + w - 1) / w;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
   }
@@ -240,6 +240,7 @@ int choose_window(int ebits) {
 // op = (nsq << 8) | idx, idx 0xff = no multiplication (trailing zeros); the first op has nsq = 0
 // and means "start from table[idx]".
 constexpr uint32_t kOpNoMul = 0xffu;
+constexpr uint32_t kOpMulOne = 0xfeu;  // fixed windows: digit 0 multiplies by the Montgomery one
 int choose_sliding_window(int ebits) {
   if (const char* f = getenv("DKG_FORCE_WINDOW")) {  // tuning/debug knob
     int w = atoi(f);
@@ -332,7 +333,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
     p.inv_mont = b.chain_s; p.chain_status = b.chain_status; p.nchain_warps = nchain;
   }
   p.bases = d_bases; p.out = d_out; p.status = d_status; p.count = count; p.in_limbs = ctx->limbs;
-  p.consts = ctx->d_consts; p.ops = ctx->d_ops; p.nops = ctx->nops; p.tab_entries = ctx->tab_entries;
+  p.consts = ctx->d_consts; p.ops = ctx->d_ops; p.nops = ctx->nops; p.tab_entries = ctx->tab_entries; p.table_odd = ctx->table_odd;
   p.negative = ctx->negative; p.n0inv = ctx->n0inv; p.scratch = d->scratch;
   p.scratch_per_warp = ctx->scratch_per_warp; p.scratch_q_offset = ctx->scratch_q_offset; p.counter = d->counter; p.final_mul = d_final_mul;
   ctx->kernel<<<ctas, ctx->warps * 32, ctx->smem, stream>>>(p);
@@ -396,7 +397,7 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::NsqParams q{};
   q.pairs_in = pairs; q.pairs_out = pairs; q.count = count; q.consts = ctx->d_nconsts; q.ops = ctx->d_ops;
-  q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
+  q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
   q.scratch_q_offset = ctx->nscratch_q_offset; q.counter = d->counter;
   ctx->nsq_kernel<<<ctas, ctx->nwarps * 32, ctx->nsmem, stream>>>(q);
   dkg::NsqIoParams x = e;
@@ -483,8 +484,31 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
 
   // window digits
   ctx->ebits = exp_limbs ? dkg_host::bit_length(exponent, exp_limbs) : 0;
-  ctx->wbits = choose_sliding_window(ctx->ebits);
-  std::vector<uint32_t> ops = sliding_window_ops(exponent, ctx->ebits, ctx->wbits, &ctx->tab_entries, &ctx->nmul);
+  // Default: fixed windows, every window multiplies (digit 0 by the Montgomery one), so the sequence
+  // of operations does not depend on the exponent's bits -- only the table index does.  Sliding
+  // windows (DKG_SLIDING_WINDOW=1) save 23 % of the multiplications (~1.5 % of the run time in the
+  // pair arithmetic) at the price of an exponent-dependent operation list, as in mpz_powm.
+  std::vector<uint32_t> ops;
+  if (const char* sw = getenv("DKG_SLIDING_WINDOW"); sw && atoi(sw) != 0) {
+    ctx->wbits = choose_sliding_window(ctx->ebits);
+    ops = sliding_window_ops(exponent, ctx->ebits, ctx->wbits, &ctx->tab_entries, &ctx->nmul);
+    ctx->table_odd = 1;
+  } else {
+    ctx->wbits = choose_window(ctx->ebits, 7);
+    const int ndigits = (ctx->ebits + ctx->wbits - 1) / ctx->wbits;
+    for (int t = 0; t < ndigits; ++t) {
+      const int lowbit = ctx->wbits * (ndigits - 1 - t);
+      unsigned dgt = 0;
+      for (int b = 0; b < ctx->wbits; ++b) {
+        const int bit = lowbit + b;
+        if (bit < ctx->ebits && ((exponent[bit / 32] >> (bit % 32)) & 1u)) dgt |= 1u << b;
+      }
+      ops.push_back(((t == 0 ? 0u : (uint32_t)ctx->wbits) << 8) | (dgt ? dgt - 1 : kOpMulOne));
+    }
+    ctx->tab_entries = ndigits ? (1 << ctx->wbits) - 1 : 0;
+    ctx->nmul = ndigits;
+    ctx->table_odd = 0;
+  }
   ctx->nops = (int)ops.size();
   if (ops.empty()) ops.push_back(0);
 

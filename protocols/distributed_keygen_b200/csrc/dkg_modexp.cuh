@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
   const V* ONEg = reinterpret_cast<const V*>(p.consts + Lp + K + Lp);
   // lane-replicated copies of R^2 and R mod N ([v][lane], after the uniform constants)
   const V* R2rep = reinterpret_cast<const V*>(p.consts + Lp + K + 3 * Lp) + lane;
+  const V* ONErep = R2rep + (size_t)LV * 32;
 
   const unsigned gwarp = blockIdx.x * nwarps + warp;
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
@@ -378,21 +379,25 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
     if (p.nops == 0) {
       for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = ONEg[v];
     } else {
-      // ---- table of odd powers: tab[k] = c^(2k+1) (Montgomery form); c^2 in the slot after ---
+      // ---- window table: tab[k] = c^(k+1), or the odd powers c^(2k+1) with c^2 in the slot after
       const int tn = p.tab_entries;
       for (int v = 0; v < LV; ++v) tab[(size_t)v * 32 + lane] = Xw[v * 32 + lane];
       if (tn > 1) {
-        V* c2 = tab + (size_t)tn * LV * 32 + lane;
-        mont_call<K, M, MONT_SQR>(io);
-        for (int v = 0; v < LV; ++v) { c2[(size_t)v * 32] = Xw[v * 32 + lane]; Xw[v * 32 + lane] = tab[(size_t)v * 32 + lane]; }
-        io.Y = c2;
+        const V* step = tab + lane;   // multiply by c ...
+        if (p.table_odd) {            // ... or by c^2
+          V* c2 = tab + (size_t)tn * LV * 32 + lane;
+          mont_call<K, M, MONT_SQR>(io);
+          for (int v = 0; v < LV; ++v) { c2[(size_t)v * 32] = Xw[v * 32 + lane]; Xw[v * 32 + lane] = tab[(size_t)v * 32 + lane]; }
+          step = c2;
+        }
+        io.Y = step;
         for (int k = 1; k < tn; ++k) {
           mont_call<K, M, MONT_MUL>(io);
           V* dst = tab + (size_t)k * LV * 32 + lane;
           for (int v = 0; v < LV; ++v) dst[(size_t)v * 32] = Xw[v * 32 + lane];
         }
       }
-      // ---- left-to-right sliding windows, one operation list for the whole batch ---------------
+      // ---- left to right through the operation list (one list for the whole batch) -------------
       {
         const V* src = tab + (size_t)(p.ops[0] & 0xffu) * LV * 32 + lane;
         for (int v = 0; v < LV; ++v) Xw[v * 32 + lane] = src[(size_t)v * 32];
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
         for (uint32_t s = op >> 8; s > 0; --s) mont_call<K, M, MONT_SQR>(io);
         const uint32_t idx = op & 0xffu;
         if (idx != 0xffu) {
-          io.Y = tab + (size_t)idx * LV * 32 + lane;
+          io.Y = idx == 0xfeu ? ONErep : tab + (size_t)idx * LV * 32 + lane;
           mont_call<K, M, MONT_MUL>(io);
         }
       }

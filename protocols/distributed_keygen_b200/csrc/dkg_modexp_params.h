@@ -35,12 +35,15 @@ struct ModexpParams {
   int in_limbs;
   // device constants: N[Lp] | NINV[K] | R2[Lp] | ONER[Lp] | R3[Lp]   (Lp = K*M)
   const uint32_t* consts;
-  // sliding-window operation list shared by the whole batch (built by the host, dkg_engine.cu):
-  // op = (nsq << 8) | idx: square nsq times, then multiply by table[idx] = c^(2 idx + 1)
-  // (idx 0xff: no multiplication); op 0 has nsq = 0 and starts from table[idx]
+  // operation list shared by the whole batch (built by the host, dkg_engine.cu):
+  // op = (nsq << 8) | idx: square nsq times, then multiply by table[idx]
+  // (idx 0xff: no multiplication, 0xfe: multiply by the Montgomery one); op 0 has nsq = 0 and
+  // starts from table[idx].  table_odd = 0: table[k] = c^(k+1) (fixed windows, the default);
+  // table_odd = 1: table[k] = c^(2k+1) (sliding windows)
   const uint32_t* ops;
   int nops;
-  int tab_entries;         // odd powers to build: c^1 .. c^(2 tab_entries - 1)
+  int tab_entries;
+  int table_odd;
   int negative;            // invert the base first
   uint32_t n0inv;          // -N^-1 mod 2^32
   uint32_t* scratch;       // per-warp table scratch

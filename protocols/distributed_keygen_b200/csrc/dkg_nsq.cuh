@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   const V* ONEA = Cg + 2 * LV, *ONEB = Cg + 3 * LV;
   // the six constants again, lane-replicated ([v][lane]) so that they can be multiplication operands
   const V* Crep = Cg + 6 * LV + lane;
-  const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32,
+  const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
+          *ONEBr = Crep + (size_t)3 * LV * 32,
           *PLAIN1r = Crep + (size_t)4 * LV * 32, *ZEROr = Crep + (size_t)5 * LV * 32;
 
   const unsigned gwarp = blockIdx.x * nwarps + warp;
@@ -170,20 +171,24 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
     if (p.nops == 0) {
       for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = ONEA[v]; Bw[v * 32 + lane] = ONEB[v]; }
     } else {
-      // table of odd powers: entry k = c^(2k+1), a at (2k)*LV*32, b right after; c^2 after the last
+      // window table: entry k = c^(k+1) (or the odd powers c^(2k+1), c^2 after the last), a at
+      // (2k)*LV*32, b right after
       const int tn = p.tab_entries;
       auto tab_a = [&](int k) -> V* { return tab + (size_t)k * 2 * LV * 32 + lane; };
       auto tab_b = [&](int k) -> V* { return tab + ((size_t)k * 2 + 1) * LV * 32 + lane; };
       for (int v = 0; v < LV; ++v) { tab_a(0)[(size_t)v * 32] = Aw[v * 32 + lane]; tab_b(0)[(size_t)v * 32] = Bw[v * 32 + lane]; }
       if (tn > 1) {
-        pair_sqr();
-        V* ca = tab_a(tn); V* cb = tab_b(tn);
-        for (int v = 0; v < LV; ++v) {
-          ca[(size_t)v * 32] = Aw[v * 32 + lane]; cb[(size_t)v * 32] = Bw[v * 32 + lane];
-          Aw[v * 32 + lane] = tab_a(0)[(size_t)v * 32]; Bw[v * 32 + lane] = tab_b(0)[(size_t)v * 32];
+        V* sa = tab_a(0); V* sb = tab_b(0);   // multiply by c ...
+        if (p.table_odd) {                    // ... or by c^2
+          pair_sqr();
+          sa = tab_a(tn); sb = tab_b(tn);
+          for (int v = 0; v < LV; ++v) {
+            sa[(size_t)v * 32] = Aw[v * 32 + lane]; sb[(size_t)v * 32] = Bw[v * 32 + lane];
+            Aw[v * 32 + lane] = tab_a(0)[(size_t)v * 32]; Bw[v * 32 + lane] = tab_b(0)[(size_t)v * 32];
+          }
         }
         for (int k = 1; k < tn; ++k) {
-          pair_mul(ca, cb);
+          pair_mul(sa, sb);
           V* da = tab_a(k); V* db = tab_b(k);
           for (int v = 0; v < LV; ++v) { da[(size_t)v * 32] = Aw[v * 32 + lane]; db[(size_t)v * 32] = Bw[v * 32 + lane]; }
         }
@@ -197,7 +202,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
         const uint32_t op = p.ops[t];
         for (uint32_t s = op >> 8; s > 0; --s) pair_sqr();
         const uint32_t idx = op & 0xffu;
-        if (idx != 0xffu) pair_mul(tab_a((int)idx), tab_b((int)idx));
+        if (idx == 0xfeu) pair_mul(ONEAr, ONEBr);
+        else if (idx != 0xffu) pair_mul(tab_a((int)idx), tab_b((int)idx));
       }
     }
     pair_mul(PLAIN1r, ZEROr);   // out of the Montgomery domain: the pair now stands for the result itself

@@ -13,8 +13,8 @@ struct NsqParams {
   //   N | NINV[K] | DNEG (= -R mod N) | R2A | R2B (pair of R^2 mod N^2) | ONEA | ONEB (pair of R mod N^2)
   //   | PLAIN1 (= 1) | ZERO
   const uint32_t* consts;
-  const uint32_t* ops;        // sliding-window operation list, see ModexpParams
-  int nops, tab_entries;
+  const uint32_t* ops;        // operation list, see ModexpParams
+  int nops, tab_entries, table_odd;
   uint32_t* scratch;
   unsigned long long scratch_per_warp;   // in uint32
   unsigned long long scratch_q_offset;

@@ -170,10 +170,13 @@ def test_ragged_batch_sizes(eng):
     ctx.close()
 
 
-def test_sliding_window_exponent_shapes(eng):
-    """Exponents that stress the operation list of the sliding windows: powers of two (only trailing
-    squarings), long zero runs (more than 255 squarings in one step), all ones (every window full),
-    alternating bits; through the generic kernel and through the pair arithmetic (N^2 with root)."""
+@pytest.mark.parametrize("sliding", ["0", "1"])
+def test_window_exponent_shapes(eng, sliding, monkeypatch):
+    """Exponents that stress the operation list, with the default fixed windows (digit 0 multiplies
+    by one) and with sliding windows (DKG_SLIDING_WINDOW=1): powers of two, long zero runs (more
+    than 255 squarings in one step), all ones, alternating bits; through the generic kernel and
+    through the pair arithmetic (N^2 with root)."""
+    monkeypatch.setenv("DKG_SLIDING_WINDOW", sliding)
     rng = random.Random(77)
     p = rng.getrandbits(130) | 1 | (1 << 129)
     q = rng.getrandbits(130) | 1 | (1 << 129)
