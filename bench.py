@@ -406,9 +406,9 @@ def main() -> None:
                 "frac": achieved / peak,
                 # DRAM bytes of one launch of this kernel: ncu dram__bytes_read.sum + dram__bytes_write.sum
                 # captured once on a 113 664-ciphertext launch (profiles/r01_ncu_nsq_traffic_final.csv:
-                # 32.82 GB + 5.13 GB, window tables spilling out of L2), scaled to this launch's size;
+                # 37.80 GB + 8.72 GB, window tables spilling out of L2), scaled to this launch's size;
                 # only known for the pair-arithmetic kernel at 2048-bit N
-                "traffic": (37.949e9 * B / 113664.0) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None,
+                "traffic": (46.523e9 * B / 113664.0) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None,
                 "traffic_unit": "bytes per launch (DRAM, from the committed ncu capture)",
                 "kernel": ("modexp_nsq_kernel<%d,%d>" % (info["pair_K"], info["pair_M"])) if info.get("pair_arithmetic")
                 else ("modexp_fixed_kernel<%d,%d>" % (info["K"], info["M"])),
