@@ -40,12 +40,30 @@ KEY_NAME = "cfg2_k2048_p3_t1_exact"
 WORKLOAD = "cfg2: 3 parties t=1 key_length=2048 (exact 2048-bit N): 3 partial decryptions + share combination per ciphertext"
 
 
-def load_key():
-    from oracle import keys as okeys
+class KeyData:
+    """The synthetic dealer key of the workload (tests/golden/dealer_vectors.json), as plain integers:
+    n, parties, t, theta and one Shamir share of lambda*beta per party."""
 
+    def __init__(self, d: dict) -> None:
+        self.json = d
+        self.n = int(d["n"], 16)
+        self.parties = int(d["parties"])
+        self.t = int(d["t"])
+        self.theta = int(d["theta"], 16)
+        self.shares = {int(i): int(v, 16) for i, v in d["shares"].items()}
+
+
+def load_key() -> KeyData:
     with open(os.path.join(ROOT, "tests", "golden", "dealer_vectors.json")) as fh:
         data = json.load(fh)
-    return okeys.dealer_key_from_json(data["keys"][KEY_NAME]["key"])
+    return KeyData(data["keys"][KEY_NAME]["key"])
+
+
+def oracle_key(dk: KeyData):
+    """The oracle's view of the same key: only the CPU-baseline / reference arm may use it."""
+    from oracle import keys as okeys
+
+    return okeys.dealer_key_from_json(dk.json)
 
 
 def canonical_modexp_macs(exp_bits: int, limbs: int) -> float:
@@ -151,6 +169,7 @@ def cpu_baseline(dk, cores: int, sample: int, seed: int, cpython: bool = True) -
     reference's CPU path with the [gmpy] extra (gmpy2.powmod wraps mpz_powm)."""
     from oracle import gmp
 
+    dk = oracle_key(dk)
     n2 = dk.n * dk.n
     limbs = (n2.bit_length() + 31) // 32
     cts = random_units(sample, n2, limbs, seed)
@@ -253,10 +272,12 @@ def main() -> None:
     dk = load_key()
     shares = 2 * dk.t + 1
     keys = {}
+    import math
+
+    n_fac = math.factorial(dk.parties)
     for pid in range(1, shares + 1):
-        k = dk.keys[pid]
-        share = eng.IntegerShares(dict(k.share.shares), k.share.degree, k.share.scaling, k.share.number_of_parties)
-        keys[pid] = eng.PaillierSharedKey(k.n, k.t, pid, share, k.theta, device=local_rank)
+        share = eng.IntegerShares({pid: dk.shares[pid]}, 2 * dk.t, n_fac * n_fac, dk.parties)
+        keys[pid] = eng.PaillierSharedKey(dk.n, dk.t, pid, share, dk.theta, device=local_rank)
     ctxs = {pid: key._modexp_ctx() for pid, key in keys.items()}
     comb = keys[1]._combine_ctx()
     L2, Ln = comb.n2_limbs, comb.n_limbs
@@ -266,7 +287,7 @@ def main() -> None:
 
     # ---- inputs: real encryptions are not needed for cost, but the result must be checkable:
     # use c = (1 + m N) * u^N style values?  r^N costs a modexp per element on the host, so take
-    # uniformly random units and check partials bit-exactly against the oracle on a sample, and
+    # uniformly random units and check partials bit-exactly against CPython pow on a sample, and
     # the combination on true encryptions in a small side batch.
     host_cts = random_units(B, dk.n * dk.n, L2, 1000 + rank)
     pinned_cts = torch.from_numpy(host_cts.view(np.int32)).pin_memory()
@@ -317,22 +338,28 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
 
-    # ---- parity spot-check of what was just timed (oracle = checker only) ---------------------
-    from oracle import gmp as ogmp
+    # ---- parity spot-check of what was just timed, against CPython integers --------------------
+    # (the full parity suite against the oracle and the reference's golden vectors is tests/)
+    from protocols.distributed_keygen_b200.limbs import limbs_to_ints
 
     part_host = d_partials.cpu().numpy().view(np.uint32)
     n2 = dk.n * dk.n
     for s, pid in enumerate(range(1, shares + 1)):
+        e = exps[pid]
         for i in (0, B // 3, B - 1):
-            c = ogmp.limbs_to_ints(host_cts[i : i + 1])[0]
-            want = dk.keys[pid].partial_decrypt(c)
-            got = ogmp.limbs_to_ints(part_host[s, i : i + 1])[0]
+            c = limbs_to_ints(host_cts[i : i + 1])[0]
+            want = pow(pow(c, -1, n2), -e, n2) if e < 0 else pow(c, e, n2)
+            got = limbs_to_ints(part_host[s, i : i + 1])[0]
             assert got == want, f"rank {rank}: partial decryption mismatch party {pid} element {i}"
     assert int(d_pstatus.max().item()) == 0 and int(d_cstatus.max().item()) == 0
     plain_host = d_plain.cpu().numpy().view(np.uint32)
+    theta_inv = pow(dk.theta, -1, dk.n)
     for i in (0, B // 2, B - 1):
-        parts_i = {pid: ogmp.limbs_to_ints(part_host[s, i : i + 1])[0] for s, pid in enumerate(range(1, shares + 1))}
-        assert ogmp.limbs_to_ints(plain_host[i : i + 1])[0] == dk.keys[1].decrypt(parts_i), "combine mismatch"
+        x = 1
+        for s in range(shares):
+            x = x * limbs_to_ints(part_host[s, i : i + 1])[0] % n2
+        assert (x - 1) % dk.n == 0, "combined value minus one not divisible by N"
+        assert limbs_to_ints(plain_host[i : i + 1])[0] == ((x - 1) // dk.n) * theta_inv % dk.n, "combine mismatch"
 
     # ---- end to end through the host-buffer API ------------------------------------------------
     e2e = None
@@ -366,8 +393,10 @@ def main() -> None:
                "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world}
 
     # ---- true encryptions through the same kernels: decrypt(encrypt(m)) == m -------------------
-    from oracle.paillier_oracle import encrypt_raw
     import random
+
+    def encrypt_raw(n, m, r):  # (1 + m N) * r^N mod N^2, g = N + 1
+        return (1 + m * n) * pow(r, n, n * n) % (n * n)
 
     rng = random.Random(7 + rank)
     ms = [rng.randrange(dk.n) for _ in range(64)]
