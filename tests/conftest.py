@@ -36,3 +36,8 @@ def dealer_vectors():
 @pytest.fixture(scope="session")
 def biprime_vectors():
     return load_golden("biprime_vectors.json")
+
+
+# scratch experiments and measurement tools live under tests/ (they use the oracle as a checker)
+# but are not test modules
+collect_ignore_glob = ["scratch/*", "tools/*"]

@@ -1,7 +1,7 @@
 // How fast can w warps per SMSP drive the multiplier pipe with the block product alone?
 #include <cstdio>
 #include <vector>
-#include "../protocols/distributed_keygen_b200/csrc/dkg_modexp.cuh"
+#include "../../protocols/distributed_keygen_b200/csrc/dkg_modexp.cuh"
 using namespace dkg;
 // variant: every row chain split in two (more independent chains, more carry counters)
 template <int K> struct ColAcc2 { uint64_t E[K + 1]; uint64_t O[K - 1]; uint32_t CE[K + 2]; uint32_t CO[K + 2]; };

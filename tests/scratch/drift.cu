@@ -1,5 +1,5 @@
 // ptxas register-drift experiments on the block product loop
-#include "../protocols/distributed_keygen_b200/csrc/dkg_modexp.cuh"
+#include "../../protocols/distributed_keygen_b200/csrc/dkg_modexp.cuh"
 using namespace dkg;
 template <int K, int M>
 struct IO2 : WarpIO<K, M> {

@@ -4,7 +4,7 @@ cfg3 (5 parties, t=2), cfg4 (key_length 4096: partial decrypt and r^N), cfg5 (bi
 sweep), plus the reference-shaped 2048-bit key.  One JSON line per measurement; device-resident
 timing with CUDA events, results spot-checked against CPython pow.
 
-    python scripts/bench_configs.py [--quick]
+    python tests/tools/bench_configs.py [--quick]
 """
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ import random
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
