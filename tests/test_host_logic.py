@@ -142,3 +142,32 @@ def test_key_blob_reader_on_reference_fixtures(fixture_vectors):
             assert key.partial_decrypt_exponent() == want.partial_decrypt_exponent()
             seen += 1
     assert seen == 24
+
+
+def test_oracle_is_test_infrastructure_only():
+    """Nothing under the product package imports oracle/, and bench.py touches it only inside the
+    CPU-baseline / reference-arm helpers (oracle_key, cpu_baseline)."""
+    import ast
+    import pathlib
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+
+    def oracle_imports(path):
+        tree = ast.parse(path.read_text())
+        found = []
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                found.append(node.lineno)
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                found.append(node.lineno)
+        return found
+
+    for path in (root / "protocols").rglob("*.py"):
+        assert oracle_imports(path) == [], f"{path} imports the oracle"
+    bench = root / "bench.py"
+    tree = ast.parse(bench.read_text())
+    allowed = set()
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("oracle_key", "cpu_baseline"):
+            allowed.update(range(node.lineno, node.end_lineno + 1))
+    assert all(line in allowed for line in oracle_imports(bench)), "bench.py uses the oracle outside the CPU-baseline leg"
