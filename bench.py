@@ -66,6 +66,19 @@ def oracle_key(dk: KeyData):
     return okeys.dealer_key_from_json(dk.json)
 
 
+def hbm_side(traffic_bytes: float, launch_ms: float) -> dict:
+    """DRAM bytes of one launch / its duration against the measured copy bandwidth of this pool's
+    B200s (MEASURED_PEAKS.json, driver-written; fallback: the profiling recipe's 6.5 TB/s)."""
+    peak, src = 6500.0, "fallback 6.5 TB/s (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak, src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    achieved = traffic_bytes / (launch_ms * 1e-3) / 1e9
+    return {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": src}
+
+
 def canonical_modexp_macs(exp_bits: int, limbs: int) -> float:
     """modmul(L) = 2L^2 + L wide-MACs; modexp(E, L) = (E + ceil(E/5) + 32)
     modmuls (squarings counted as multiplies, canonical window 5)."""
@@ -439,6 +452,8 @@ def main() -> None:
                 # only known for the pair-arithmetic kernel at 2048-bit N
                 "traffic": (46.523e9 * B / 113664.0) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None,
                 "traffic_unit": "bytes per launch (DRAM, from the committed ncu capture)",
+                # the HBM side of the roofline, to show the kernel is nowhere near it
+                "hbm": hbm_side(46.523e9 * B / 113664.0, avg_ms) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None,
                 "kernel": ("modexp_nsq_kernel<%d,%d>" % (info["pair_K"], info["pair_M"])) if info.get("pair_arithmetic")
                 else ("modexp_fixed_kernel<%d,%d>" % (info["K"], info["M"])),
                 "actual_wide_mac": actual, "frac_actual": actual / peak,
