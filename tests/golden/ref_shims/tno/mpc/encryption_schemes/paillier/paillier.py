@@ -21,10 +21,12 @@ class Paillier:
 
         prec: int
 
-    def __init__(self, public_key: Any = None, secret_key: Any = None, precision: int = 0, **_kwargs: Any) -> None:
+    def __init__(self, public_key: Any = None, secret_key: Any = None, precision: int = 0,
+                 share_secret_key: bool = False, **_kwargs: Any) -> None:
         self.public_key = public_key
         self.secret_key = secret_key
         self.precision = precision
+        self.share_secret_key = share_secret_key
 
 
 class PaillierCiphertext:
