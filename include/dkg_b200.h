@@ -68,6 +68,17 @@ int dkg_device_count(int* count);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long dkg_launch_count(void);
 
+/* Process-wide settings (initialised from the environment when first needed, never re-read):
+ *   "coop_max"         largest batch a fixed-modulus N^2 context created FROM NOW ON routes to the
+ *                      cooperative warp-per-ciphertext kernels (csrc/dkg_coop.cuh), the latency path
+ *                      of PaillierSharedKey.partial_decrypt on one / a few ciphertexts
+ *                      (distributed_keygen.py:314-382); 0 disables it.  Environment: DKG_COOP_MAX,
+ *                      DKG_COOP=0.
+ *   "coop_grouped_max" same for the grouped (biprimality) entry points, per call.  Environment:
+ *                      DKG_COOP_GROUPED_MAX. */
+int dkg_config_set(const char* key, long value);
+int dkg_config_get(const char* key, long* value);
+
 /* Register-resident mad.wide.u32 microbenchmark: wide multiply-accumulates per second of the
  * integer multiplier on `device`, plain (no carry) and carry-chained.  The roofline denominator. */
 int dkg_measure_imad_peak(int device, double* plain_wide_mac_per_s, double* carry_wide_mac_per_s);

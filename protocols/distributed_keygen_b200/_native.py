@@ -27,7 +27,7 @@ STATUS_NOT_DIVISIBLE = 2
 # every symbol include/dkg_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "dkg_version", "dkg_last_error", "dkg_device_count", "dkg_launch_count",
-    "dkg_measure_imad_peak",
+    "dkg_measure_imad_peak", "dkg_config_set", "dkg_config_get",
     "dkg_modexp_ctx_create", "dkg_modexp_ctx_create_nsq", "dkg_modexp_ctx_destroy", "dkg_modexp_ctx_info",
     "dkg_modexp_batch", "dkg_modexp_batch_device",
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
@@ -57,6 +57,8 @@ def _load() -> ctypes.CDLL:
     lib.dkg_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
     lib.dkg_launch_count.restype = ctypes.c_ulonglong
     lib.dkg_measure_imad_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.dkg_config_set.argtypes = [ctypes.c_char_p, ctypes.c_long]
+    lib.dkg_config_get.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_long)]
     lib.dkg_modexp_ctx_create.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void)]
     lib.dkg_modexp_ctx_create_nsq.argtypes = [ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_void)]
     lib.dkg_modexp_ctx_destroy.argtypes = [c_void]
@@ -90,6 +92,16 @@ def check(rc: int) -> None:
     if rc != DKG_OK:
         msg = lib.dkg_last_error()
         raise DkgError(rc, msg.decode() if msg else "")
+
+
+def config_set(key: str, value: int) -> None:
+    check(lib.dkg_config_set(key.encode(), int(value)))
+
+
+def config_get(key: str) -> int:
+    v = ctypes.c_long(0)
+    check(lib.dkg_config_get(key.encode(), ctypes.byref(v)))
+    return int(v.value)
 
 
 def device_count() -> int:

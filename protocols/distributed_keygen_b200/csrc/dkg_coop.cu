@@ -1,0 +1,37 @@
+// Instantiations and launchers of the cooperative (warp-per-operand) kernels, dkg_coop.cuh.
+#include "dkg_coop.cuh"
+
+namespace dkg {
+
+// K = 6: up to 96 limbs per component, 16 warps per CTA; K = 12: up to 192 limbs, 8 warps.
+int coop_max_warps(int K) { return K == 6 ? 16 : 8; }
+
+template <int K, int THREADS>
+static cudaError_t launch_nsq_t(const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
+  auto kernel = coop_nsq_kernel<K, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<ctas, warps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+template <int K, int THREADS>
+static cudaError_t launch_grouped_t(const CoopGroupedParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
+  auto kernel = coop_grouped_kernel<K, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<ctas, warps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_coop_nsq(int K, const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
+  if (K == 6) return launch_nsq_t<6, 512>(p, ctas, warps, smem, stream);
+  if (K == 12) return launch_nsq_t<12, 256>(p, ctas, warps, smem, stream);
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_coop_grouped(int K, const CoopGroupedParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
+  if (K == 6) return launch_grouped_t<6, 512>(p, ctas, warps, smem, stream);
+  if (K == 12) return launch_grouped_t<12, 256>(p, ctas, warps, smem, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace dkg

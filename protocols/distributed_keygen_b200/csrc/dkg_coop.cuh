@@ -1,0 +1,742 @@
+// Cooperative (warp-per-operand) modular exponentiation: the latency path for small batches.
+//
+// The throughput kernels (dkg_modexp.cuh, dkg_nsq.cuh, dkg_grouped.cuh) hold one big integer per
+// THREAD, so one wave of 56 832 instances is also the latency of a single instance (0.74 s at
+// 2048-bit N).  The reference decrypts ONE ciphertext per call in _decrypt_raw
+// (distributed_keygen.py:314-382), ten in its own tests (test_distributed_keygen.py:161-185), and a
+// compute_modulus round has a handful of surviving candidates (:1288-1329): for those sizes one
+// integer is spread over the 32 lanes of a WARP here.
+//
+//  * A number of nb blocks of K limbs (K = 6 or 12, nb <= 16) lives with block p on lane p.
+//  * Product: lane d forms the block anti-diagonal sum E_d = sum_{i+j=d} X_i * Y_j with the same
+//    register-resident K x K block product as the throughput kernels (ColAcc / block_mac, all
+//    IMAD.WIDE carry chains), operands read from shared memory.  The 2nb-1 diagonals have 1..nb
+//    tiles; the spare lanes take a second..fourth chunk of the long ones (host-built plan,
+//    tests/coop_model.py: make_plan) and hand their partial sums over with __shfl_sync.
+//  * Carry resolution: E_d overlaps E_{d-1}, E_{d-2}; lane d fetches the overlapping limbs with
+//    __shfl_up_sync, adds, passes its small carry up once and settles the remaining 0/1 ripple
+//    with two __ballot_sync masks (generate / propagate) and one integer addition.
+//  * Montgomery product in three such phases: T = X*Y, q = (T mod R) * (-N^-1) mod R (low
+//    diagonals only), (T + q*N) / R.  R = 2^(32 K nb) >= 4N (>= 8N for the pair arithmetic), so no
+//    conditional subtraction is needed between products.
+//  * On top: the pair arithmetic modulo N^2 of dkg_nsq.cuh (same formulas, same bounds), with
+//    negative exponents handled per instance by the almost-inverse (Kaliski) modulo N on lane
+//    registers plus one Newton step in the pair domain -- no chains, exact per-element status;
+//    and a grouped kernel (per-instance modulus and exponent, biprimality test) that derives
+//    -N^-1 mod R, R mod N and R^2 mod N itself.
+// Python model of every lane-level step: tests/coop_model.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dkg_coop_params.h"
+#include "dkg_mont.cuh"
+
+namespace dkg {
+
+namespace coop {
+
+using sa = uint32_t;   // shared-space byte address (numbers live in shared memory; the arithmetic
+                       // below crosses noinline calls, where generic pointers would lose LDS/STS)
+__device__ __forceinline__ sa saddr(const void* p) { return (sa)__cvta_generic_to_shared(p); }
+
+template <int K>
+struct NoIO {
+  static constexpr int VW = 2;
+  struct Prefetch {};
+  __device__ __forceinline__ void prefetch_load(const Prefetch&, int, uint32_t (&)[K]) const {}
+};
+
+template <int K>
+__device__ __forceinline__ void lds(uint32_t (&r)[K], sa p) {
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int v = 0; v < K / 4; ++v)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(r[4 * v]), "=r"(r[4 * v + 1]), "=r"(r[4 * v + 2]), "=r"(r[4 * v + 3]) : "r"(p + 16u * v) : "memory");
+  } else {
+#pragma unroll
+    for (int v = 0; v < K / 2; ++v)
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[2 * v]), "=r"(r[2 * v + 1]) : "r"(p + 8u * v) : "memory");
+  }
+}
+template <int K>
+__device__ __forceinline__ void sts(sa p, const uint32_t (&r)[K]) {
+#pragma unroll
+  for (int v = 0; v < K / 2; ++v)
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(p + 8u * v), "r"(r[2 * v]), "r"(r[2 * v + 1]) : "memory");
+}
+__device__ __forceinline__ uint32_t lds1(sa p) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p) : "memory");
+  return v;
+}
+
+// this lane's entry of a plan table
+struct LanePlan {
+  int d, i0, i1, p0, p1, p2, rounds, ndiag;
+  __device__ __forceinline__ void load(const CoopPlanTable& t, int lane) {
+    d = t.d[lane]; i0 = t.i0[lane]; i1 = t.i1[lane];
+    p0 = t.partner[0][lane]; p1 = t.partner[1][lane]; p2 = t.partner[2][lane];
+    rounds = t.rounds; ndiag = t.ndiag;
+  }
+};
+
+// E_d on the primary lanes (2K+2 limbs), zero elsewhere.  X, Y (and the optional second pair, X2 != 0)
+// are nb-block numbers in shared memory.
+template <int K>
+__device__ __forceinline__ void product(uint32_t (&e)[2 * K + 2], const LanePlan& lp, int lane, sa X, sa Y, sa X2, sa Y2) {
+  ColAcc<K> a;
+#pragma unroll
+  for (int p = 0; p < 2 * K + 2; ++p) e[p] = 0;
+  acc_load<K>(a, e);
+  acc_clear_side<K>(a);
+  const NoIO<K> io;
+  const typename NoIO<K>::Prefetch pf;
+  for (int i = lp.i0; i < lp.i1; ++i) {
+    uint32_t xb[K], yb[K];
+    lds<K>(xb, X + (uint32_t)(i * K * 4));
+    lds<K>(yb, Y + (uint32_t)((lp.d - i) * K * 4));
+    block_mac<K>(a, xb, yb, io, pf);
+    if (X2 != 0) {
+      lds<K>(xb, X2 + (uint32_t)(i * K * 4));
+      lds<K>(yb, Y2 + (uint32_t)((lp.d - i) * K * 4));
+      block_mac<K>(a, xb, yb, io, pf);
+    }
+  }
+  __syncwarp();
+  acc_merge<K>(a, e);
+  for (int r = 0; r < lp.rounds; ++r) {
+    const int src = r == 0 ? lp.p0 : (r == 1 ? lp.p1 : lp.p2);
+    const int from = src >= 0 ? src : lane;
+    const uint32_t m = src >= 0 ? 0xffffffffu : 0u;
+    uint32_t t[2 * K + 2];
+#pragma unroll
+    for (int k = 0; k < 2 * K + 2; ++k) t[k] = __shfl_sync(kCoopFull, e[k], from) & m;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * K + 2; ++k) {
+      const uint64_t s = (uint64_t)e[k] + t[k] + carry;
+      e[k] = (uint32_t)s;
+      carry = (uint32_t)(s >> 32);
+    }
+  }
+  if (lane >= lp.ndiag) {
+#pragma unroll
+    for (int k = 0; k < 2 * K + 2; ++k) e[k] = 0;
+  }
+}
+
+// carry into every lane from generate / propagate masks; bit 32+ = carry out of lane 31
+__device__ __forceinline__ uint64_t lookahead(uint32_t g, uint32_t p) {
+  const uint64_t a = (uint64_t)(g | p), b = (uint64_t)g;
+  return (a + b) ^ a ^ b;
+}
+
+// s (block `lane` of sum_d E_d W^d [+ addend]) from the diagonal sums: overlap limbs by shuffle,
+// one explicit carry hop, then generate/propagate lookahead.
+template <int K>
+__device__ __forceinline__ void resolve(uint32_t (&s)[K], const uint32_t (&e)[2 * K + 2], const uint32_t* addend, int lane) {
+  uint32_t mid[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    mid[k] = __shfl_up_sync(kCoopFull, e[K + k], 1);
+    if (lane < 1) mid[k] = 0;
+  }
+  uint32_t h0 = __shfl_up_sync(kCoopFull, e[2 * K], 2), h1 = __shfl_up_sync(kCoopFull, e[2 * K + 1], 2);
+  if (lane < 2) { h0 = 0; h1 = 0; }
+  uint32_t c = 0;
+  {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint64_t t = (uint64_t)e[k] + mid[k] + carry;
+      s[k] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+    c += carry;
+    carry = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint64_t t = (uint64_t)s[k] + (k == 0 ? h0 : (k == 1 ? h1 : 0u)) + carry;
+      s[k] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+    c += carry;
+    if (addend != nullptr) {
+      carry = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const uint64_t t = (uint64_t)s[k] + addend[k] + carry;
+        s[k] = (uint32_t)t;
+        carry = (uint32_t)(t >> 32);
+      }
+      c += carry;
+    }
+  }
+  uint32_t cin = __shfl_up_sync(kCoopFull, c, 1);
+  if (lane < 1) cin = 0;
+  uint32_t g = 0, ones = 0xffffffffu;
+  {
+    uint32_t carry = cin;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint64_t t = (uint64_t)s[k] + carry;
+      s[k] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+      ones &= s[k];
+    }
+    g = carry;
+  }
+  const uint32_t G = __ballot_sync(kCoopFull, g != 0);
+  const uint32_t P = __ballot_sync(kCoopFull, ones == 0xffffffffu && g == 0);
+  uint32_t carry = (uint32_t)((lookahead(G, P) >> lane) & 1u);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint64_t t = (uint64_t)s[k] + carry;
+    s[k] = (uint32_t)t;
+    carry = (uint32_t)(t >> 32);
+  }
+}
+
+// s = x + y + (cin0 at lane 0) over the lanes; x, y must be zero on lanes >= nb.  Returns the carry
+// out of block nb-1.
+template <int K>
+__device__ __forceinline__ uint32_t add(uint32_t (&s)[K], const uint32_t (&x)[K], const uint32_t (&y)[K], uint32_t cin0,
+                                        int lane, int nb) {
+  uint32_t carry = lane == 0 ? cin0 : 0u, ones = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint64_t t = (uint64_t)x[k] + y[k] + carry;
+    s[k] = (uint32_t)t;
+    carry = (uint32_t)(t >> 32);
+    ones &= s[k];
+  }
+  const uint32_t g = carry;
+  const uint32_t G = __ballot_sync(kCoopFull, g != 0);
+  const uint32_t P = __ballot_sync(kCoopFull, ones == 0xffffffffu && g == 0 && lane < nb);
+  const uint64_t la = lookahead(G, P);
+  carry = (uint32_t)((la >> lane) & 1u);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint64_t t = (uint64_t)s[k] + carry;
+    s[k] = (uint32_t)t;
+    carry = (uint32_t)(t >> 32);
+  }
+  if (lane >= nb) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) s[k] = 0;
+  }
+  return (uint32_t)((la >> nb) & 1u);
+}
+
+// s = x - y over the lanes (mod W^nb); returns 1 if x >= y (no borrow), else 0
+template <int K>
+__device__ __forceinline__ uint32_t sub(uint32_t (&s)[K], const uint32_t (&x)[K], const uint32_t (&y)[K], int lane, int nb) {
+  uint32_t yc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) yc[k] = lane < nb ? ~y[k] : 0u;
+  return add<K>(s, x, yc, 1u, lane, nb);
+}
+
+// x > y over the lanes
+template <int K>
+__device__ __forceinline__ bool greater(const uint32_t (&x)[K], const uint32_t (&y)[K]) {
+  int gt = 0, lt = 0;
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k) {
+    if (!gt && !lt) { gt = x[k] > y[k]; lt = x[k] < y[k]; }
+  }
+  return __ballot_sync(kCoopFull, gt) > __ballot_sync(kCoopFull, lt);
+}
+template <int K>
+__device__ __forceinline__ bool is_zero(const uint32_t (&x)[K]) {
+  uint32_t nz = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) nz |= x[k];
+  return __ballot_sync(kCoopFull, nz != 0) == 0u;
+}
+template <int K>
+__device__ __forceinline__ void shr1(uint32_t (&x)[K], int lane) {
+  uint32_t in = __shfl_down_sync(kCoopFull, x[0], 1);
+  if (lane == 31) in = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) x[k] = (x[k] >> 1) | ((k + 1 < K ? x[k + 1] : in) << 31);
+}
+template <int K>
+__device__ __forceinline__ void shl1(uint32_t (&x)[K], int lane) {
+  uint32_t in = __shfl_up_sync(kCoopFull, x[K - 1], 1);
+  if (lane == 0) in = 0;
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k) x[k] = (x[k] << 1) | ((k > 0 ? x[k - 1] : in) >> 31);
+}
+
+// x <- 2x mod n for x < n (one conditional subtraction)
+template <int K>
+__device__ __forceinline__ void double_mod(uint32_t (&x)[K], const uint32_t (&n)[K], int lane, int nb) {
+  uint32_t t[K];
+  shl1<K>(x, lane);
+  if (sub<K>(t, x, n, lane, nb)) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = t[k];
+  }
+}
+
+// Per-warp working set (passed BY VALUE across the noinline calls: it stays in registers).  All
+// numbers are nb*K limbs in shared memory.
+template <int K>
+struct Warp {
+  int lane, nb;
+  LanePlan pf, pl;
+  sa N;    // modulus
+  sa NI;   // -N^-1 mod R
+  sa T;    // 2*nb*K words of scratch: T (low half of the product being reduced) | Q (quotient)
+
+  __device__ __forceinline__ sa Q() const { return T + (uint32_t)(nb * K * 4); }
+  __device__ __forceinline__ void load_block(uint32_t (&r)[K], sa num) const {
+    if (lane < nb) lds<K>(r, num + (uint32_t)(lane * K * 4));
+    else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) r[k] = 0;
+    }
+  }
+  __device__ __forceinline__ void store_block(sa num, const uint32_t (&r)[K]) const {
+    if (lane < nb) sts<K>(num + (uint32_t)(lane * K * 4), r);
+  }
+  // low nb blocks of X*Y -> out (registers, block `lane`); lanes >= nb hold garbage
+  __device__ __forceinline__ void mul_low(uint32_t (&out)[K], sa X, sa Y) const {
+    uint32_t e[2 * K + 2];
+    product<K>(e, pl, lane, X, Y, 0, 0);
+    resolve<K>(out, e, nullptr, lane);
+  }
+};
+
+// out <- (X1*Y1 [+ X2*Y2]) / R mod N, or, with X1 == 0, the Montgomery reduction of the 2nb-block
+// number already lying in w.T (T | Q area).  out may alias any operand.  The quotient q
+// ((T + q N) / R exactly) is left in w.Q().  ONE instance of the three product phases per kernel.
+template <int K>
+__device__ __noinline__ void montmul(const Warp<K> w, sa out, sa X1, sa Y1, sa X2, sa Y2) {
+  const int lane = w.lane, nb = w.nb;
+  uint32_t e[2 * K + 2], t[K], q[K], u[K];
+  if (X1 != 0) {
+    product<K>(e, w.pf, lane, X1, Y1, X2, Y2);
+    resolve<K>(t, e, nullptr, lane);
+    if (lane < nb) sts<K>(w.T + (uint32_t)(lane * K * 4), t);
+  } else {
+    if (lane < 2 * nb) lds<K>(t, w.T + (uint32_t)(lane * K * 4));
+    else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = 0;
+    }
+  }
+  __syncwarp();
+  product<K>(e, w.pl, lane, w.T, w.NI, 0, 0);
+  resolve<K>(q, e, nullptr, lane);
+  if (lane < nb) sts<K>(w.Q() + (uint32_t)(lane * K * 4), q);
+  __syncwarp();
+  product<K>(e, w.pf, lane, w.Q(), w.N, 0, 0);
+  resolve<K>(u, e, t, lane);
+  if (lane >= nb && lane < 2 * nb) sts<K>(out + (uint32_t)((lane - nb) * K * 4), u);
+  __syncwarp();
+}
+
+// dst <- b2 - m kept in [0, R) congruent modulo N (pair_fixup of dkg_nsq.cuh): S = b2 + (R - m);
+// if that passes R drop R, else add (-R mod N) and take N off once if that passes R.
+template <int K>
+__device__ __noinline__ void fixup(const Warp<K> w, sa dst, sa b2, sa m, sa dneg) {
+  uint32_t x[K], y[K], s[K];
+  w.load_block(x, b2);
+  w.load_block(y, m);
+  const uint32_t ge = sub<K>(s, x, y, w.lane, w.nb);   // b2 + ~m + 1: carry <=> S >= R
+  if (!ge) {
+    w.load_block(y, dneg);
+    const uint32_t c2 = add<K>(x, s, y, 0u, w.lane, w.nb);
+    if (c2) {
+      w.load_block(y, w.N);
+      sub<K>(s, x, y, w.lane, w.nb);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) s[k] = x[k];
+    }
+  }
+  w.store_block(dst, s);
+  __syncwarp();
+}
+
+// Pair state (A, B) in shared memory plus scratch A2 (2A).
+struct PairAddr {
+  sa A, B, A2, dneg;
+};
+
+// (A, B) <- (A, B) * (C, D)
+template <int K>
+__device__ __noinline__ void pair_mul(const Warp<K> w, const PairAddr pr, sa C, sa D) {
+  montmul<K>(w, pr.B, pr.B, C, pr.A, D);   // B <- REDC(B c + A d)
+  montmul<K>(w, pr.A, pr.A, C, 0, 0);      // A <- REDC(A c), quotient m in Q
+  fixup<K>(w, pr.B, pr.B, w.Q(), pr.dneg);
+}
+template <int K>
+__device__ __noinline__ void pair_sqr(const Warp<K> w, const PairAddr pr) {
+  uint32_t x[K];
+  w.load_block(x, pr.A);
+  shl1<K>(x, w.lane);                      // A < 2N <= R/4: no bit is lost
+  w.store_block(pr.A2, x);
+  __syncwarp();
+  montmul<K>(w, pr.B, pr.A2, pr.B, 0, 0);  // B <- REDC(2 A B)
+  montmul<K>(w, pr.A, pr.A, pr.A, 0, 0);   // A <- REDC(A^2), quotient m in Q
+  fixup<K>(w, pr.B, pr.B, w.Q(), pr.dneg);
+}
+
+// Almost-inverse (Kaliski 1995) of the plain value in `src` modulo N, on lane registers:
+//   u = N, v = a, r = 0, s = 1;  while v > 0: halve the even one / subtract the smaller from the
+//   larger and halve, doubling the other cofactor;  ends with u = gcd and r = -a^-1 2^k (mod N).
+// Then x = (N - r) 2^-k by one or two Montgomery reductions of (N - r) << (m - k).  Writes the
+// inverse (< 2N) to dst and returns true, or returns false if gcd(a, N) != 1.
+template <int K>
+__device__ __noinline__ bool mod_inverse(const Warp<K> w, sa dst, sa src) {
+  const int lane = w.lane, nb = w.nb;
+  uint32_t u[K], v[K], r[K], s[K], t[K], nreg[K];
+  w.load_block(nreg, w.N);
+  w.load_block(v, src);
+#pragma unroll
+  for (int k = 0; k < K; ++k) { u[k] = nreg[k]; r[k] = 0; s[k] = 0; }
+  if (lane == 0) s[0] = 1;
+  int k2 = 0;
+  while (!is_zero<K>(v)) {
+    const uint32_t u0 = __shfl_sync(kCoopFull, u[0], 0), v0 = __shfl_sync(kCoopFull, v[0], 0);
+    if ((u0 & 1u) == 0) { shr1<K>(u, lane); shl1<K>(s, lane); }
+    else if ((v0 & 1u) == 0) { shr1<K>(v, lane); shl1<K>(r, lane); }
+    else if (greater<K>(u, v)) {
+      sub<K>(t, u, v, lane, nb);
+#pragma unroll
+      for (int k = 0; k < K; ++k) u[k] = t[k];
+      shr1<K>(u, lane);
+      add<K>(t, r, s, 0u, lane, nb);
+#pragma unroll
+      for (int k = 0; k < K; ++k) r[k] = t[k];
+      shl1<K>(s, lane);
+    } else {
+      sub<K>(t, v, u, lane, nb);
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[k] = t[k];
+      shr1<K>(v, lane);
+      add<K>(t, s, r, 0u, lane, nb);
+#pragma unroll
+      for (int k = 0; k < K; ++k) s[k] = t[k];
+      shl1<K>(r, lane);
+    }
+    ++k2;
+  }
+  // u == 1 ?
+  {
+    uint32_t rest = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) rest |= (lane == 0 && k == 0) ? (u[k] ^ 1u) : u[k];
+    if (__ballot_sync(kCoopFull, rest != 0) != 0u) return false;
+  }
+  // r < 2N: bring below N, y = N - r
+  if (sub<K>(t, r, nreg, lane, nb)) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) r[k] = t[k];
+  }
+  sub<K>(t, nreg, r, lane, nb);     // y = N - r in (0, N]
+  const int m = 32 * K * nb, L2 = 2 * nb * K;
+  for (int pass = 0; pass < 2; ++pass) {
+    int sh;
+    if (k2 > m) { sh = 0; k2 -= m; }      // first y <- REDC(y) = y 2^-m
+    else { sh = m - k2; k2 = 0; pass = 1; }
+    // T = y << sh as 2nb blocks, through the warp's T | Q area
+    if (lane < nb) sts<K>(w.T + (uint32_t)(lane * K * 4), t);
+    else if (lane < 2 * nb) {
+      uint32_t z[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) z[k] = 0;
+      sts<K>(w.T + (uint32_t)(lane * K * 4), z);
+    }
+    __syncwarp();
+    const int ws = sh >> 5, bs = sh & 31;
+    uint32_t tb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int g = lane * K + k - ws;
+      const uint32_t hi = (g >= 0 && g < L2) ? lds1(w.T + (uint32_t)(g * 4)) : 0u;
+      const uint32_t lo = (g - 1 >= 0 && g - 1 < L2) ? lds1(w.T + (uint32_t)((g - 1) * 4)) : 0u;
+      tb[k] = bs ? ((hi << bs) | (lo >> (32 - bs))) : hi;
+    }
+    __syncwarp();
+    if (lane < 2 * nb) sts<K>(w.T + (uint32_t)(lane * K * 4), tb);
+    __syncwarp();
+    montmul<K>(w, dst, 0, 0, 0, 0);
+    w.load_block(t, dst);
+  }
+  return true;
+}
+
+}  // namespace coop
+
+// ---- pair-arithmetic exponentiation, one instance per warp ------------------------------------------
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p) {
+  using namespace coop;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* S = reinterpret_cast<uint32_t*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nb = p.nb, Lc = nb * K;
+  // CTA: the constants; per warp: A B A2 T Q C D XA XB YA YB I0
+  for (int i = threadIdx.x; i < kCoopNsqConsts * Lc; i += blockDim.x) S[i] = p.consts[i];
+  __syncthreads();
+  const uint32_t *cONEA = S + 5 * Lc;
+  const sa c0 = saddr(S), LB = (uint32_t)(Lc * 4);
+  const sa sN = c0, sNI = c0 + LB, sDNEG = c0 + 2 * LB, sR2A = c0 + 3 * LB, sR2B = c0 + 4 * LB, sONEA = c0 + 5 * LB,
+           sONEB = c0 + 6 * LB, sTWOA = c0 + 7 * LB, sTWOB = c0 + 8 * LB, sPLAIN1 = c0 + 9 * LB, sZERO = c0 + 10 * LB;
+  uint32_t* W = S + kCoopNsqConsts * Lc + (size_t)warp * 12 * Lc;
+  uint32_t *A = W, *B = W + Lc, *C = W + 5 * Lc, *XA = W + 7 * Lc, *YA = W + 9 * Lc, *I0 = W + 11 * Lc;
+  const sa w0 = saddr(W);
+  const sa sA = w0, sB = w0 + LB, sA2 = w0 + 2 * LB, sT = w0 + 3 * LB, sC = w0 + 5 * LB, sD = w0 + 6 * LB,
+           sXA = w0 + 7 * LB, sXB = w0 + 8 * LB, sYA = w0 + 9 * LB, sYB = w0 + 10 * LB, sI0 = w0 + 11 * LB;
+
+  Warp<K> w;
+  w.lane = lane; w.nb = nb; w.pf.load(p.full, lane); w.pl.load(p.low, lane);
+  w.N = sN; w.NI = sNI; w.T = sT;
+  PairAddr pr;
+  pr.A = sA; pr.B = sB; pr.A2 = sA2; pr.dneg = sDNEG;
+
+  const unsigned gwarp = blockIdx.x * nwarps + warp;
+  uint32_t* tab = p.scratch + (size_t)gwarp * p.scratch_per_warp;   // entry k: a at 2k*Lc, b right after
+  auto copy = [&](uint32_t* dst, const uint32_t* src, int n) {
+    for (int l = lane; l < n; l += 32) dst[l] = src[l];
+  };
+
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(p.counter, 1u);
+    idx = __shfl_sync(kCoopFull, idx, 0);
+    if (idx >= p.count) break;
+    copy(A, p.pairs_in + idx * (unsigned long long)(2 * Lc), 2 * Lc);   // A | B contiguous
+    __syncwarp();
+    bool ok = true;
+    if (p.negative) { copy(I0, A, Lc); __syncwarp(); }
+    pair_mul<K>(w, pr, sR2A, sR2B);             // into the Montgomery domain: x R
+    if (p.negative) {
+      // x^-1 = y0 (2 - x y0) with y0 = (x mod N)^-1 taken modulo N: one Newton step modulo N^2
+      copy(XA, A, 2 * Lc); __syncwarp();        // XA | XB
+      ok = mod_inverse<K>(w, sI0, sI0);
+      if (ok) {
+        copy(A, I0, Lc);
+        for (int l = lane; l < Lc; l += 32) B[l] = 0;
+        __syncwarp();
+        pair_mul<K>(w, pr, sR2A, sR2B);         // P(y0)
+        copy(YA, A, 2 * Lc); __syncwarp();
+        pair_mul<K>(w, pr, sXA, sXB);           // P(x y0) = P(1 + t N)
+        {
+          uint32_t x[K], y[K], s[K];
+          w.load_block(x, sTWOA);
+          w.load_block(y, sA);
+          sub<K>(s, x, y, lane, nb);            // (2 ONE_a + 2N) - z_a in (0, 4N)
+          w.store_block(sA, s);
+          __syncwarp();
+        }
+        fixup<K>(w, sB, sTWOB, sB, sDNEG);      // (2 ONE_b - 2R) - z_b
+        pair_mul<K>(w, pr, sYA, sYB);           // P(x^-1)
+      }
+    }
+    if (ok) {
+      if (p.nops == 0) {
+        copy(A, cONEA, 2 * Lc); __syncwarp();   // ONEA | ONEB contiguous
+      } else {
+        const int tn = p.tab_entries;
+        auto entry = [&](int k) -> uint32_t* { return tab + (size_t)k * 2 * Lc; };
+        copy(entry(0), A, 2 * Lc);
+        if (tn > 1) {
+          int src = 0;
+          if (p.table_odd) {                    // odd powers: multiply by c^2, kept after the last entry
+            pair_sqr<K>(w, pr);
+            copy(entry(tn), A, 2 * Lc);
+            __syncwarp();
+            copy(A, entry(0), 2 * Lc);
+            src = tn;
+          }
+          __syncwarp();
+          copy(C, entry(src), 2 * Lc);          // C | D contiguous
+          __syncwarp();
+          for (int k = 1; k < tn; ++k) {
+            pair_mul<K>(w, pr, sC, sD);
+            copy(entry(k), A, 2 * Lc);
+          }
+        }
+        __syncwarp();
+        copy(A, entry((int)(p.ops[0] & 0xffu)), 2 * Lc);
+        __syncwarp();
+        for (int t = 1; t < p.nops; ++t) {
+          const uint32_t op = p.ops[t];
+          for (uint32_t q = op >> 8; q > 0; --q) pair_sqr<K>(w, pr);
+          const uint32_t di = op & 0xffu;
+          if (di == 0xfeu) pair_mul<K>(w, pr, sONEA, sONEB);
+          else if (di != 0xffu) {
+            copy(C, entry((int)di), 2 * Lc);
+            __syncwarp();
+            pair_mul<K>(w, pr, sC, sD);
+          }
+        }
+      }
+      pair_mul<K>(w, pr, sPLAIN1, sZERO);       // out of the Montgomery domain
+      copy(p.pairs_out + idx * (unsigned long long)(2 * Lc), A, 2 * Lc);
+    } else {
+      for (int l = lane; l < 2 * Lc; l += 32) p.pairs_out[idx * (unsigned long long)(2 * Lc) + l] = 0;
+    }
+    if (p.status != nullptr && lane == 0) p.status[idx] = ok ? 0 : 1;
+    __syncwarp();
+  }
+}
+
+// ---- grouped exponentiation (per-instance modulus and exponent), one instance per warp ---------------
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS) coop_grouped_kernel(const CoopGroupedParams p) {
+  using namespace coop;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nb = p.nb, Lc = nb * K;
+  // per warp: N NI X T Q Y R2 ONE U
+  uint32_t* W = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * 9 * Lc;
+  uint32_t *N = W, *X = W + 2 * Lc, *Y = W + 5 * Lc, *ONE = W + 7 * Lc;
+  const sa w0 = saddr(W), LB = (uint32_t)(Lc * 4);
+  const sa sN = w0, sNI = w0 + LB, sX = w0 + 2 * LB, sT = w0 + 3 * LB, sY = w0 + 5 * LB, sR2 = w0 + 6 * LB,
+           sONE = w0 + 7 * LB, sU = w0 + 8 * LB;
+  Warp<K> w;
+  w.lane = lane; w.nb = nb; w.pf.load(p.full, lane); w.pl.load(p.low, lane);
+  w.N = sN; w.NI = sNI; w.T = sT;
+  const unsigned gwarp = blockIdx.x * nwarps + warp;
+  uint32_t* tab = p.scratch + (size_t)gwarp * p.scratch_per_warp;   // entry k (value x^(k+1)) at k*Lc
+  auto copy = [&](uint32_t* dst, const uint32_t* src, int n) {
+    for (int l = lane; l < n; l += 32) dst[l] = src[l];
+  };
+  const unsigned long long count = p.groups * (unsigned long long)p.per_group;
+  const int m = 32 * Lc;
+
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(p.counter, 1u);
+    idx = __shfl_sync(kCoopFull, idx, 0);
+    if (idx >= count) break;
+    const unsigned long long g = idx / (unsigned long long)p.per_group;
+    const uint32_t* mod = p.moduli + g * (unsigned long long)p.limbs;
+    const uint32_t* base = p.bases + idx * (unsigned long long)p.limbs;
+    for (int l = lane; l < Lc; l += 32) {
+      N[l] = l < p.limbs ? mod[l] : 0u;
+      X[l] = l < p.limbs ? base[l] : 0u;
+    }
+    __syncwarp();
+    uint32_t nreg[K], x[K], t[K];
+    w.load_block(nreg, sN);
+    // ---- -N^-1 mod R by Newton: inv <- inv (2 - N inv), precision doubling from 32 bits
+    {
+      const uint32_t n0 = N[0];
+      uint32_t inv0 = n0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) inv0 *= 2u - n0 * inv0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = (lane == 0 && k == 0) ? inv0 : 0u;
+      w.store_block(sNI, x);
+      __syncwarp();
+      uint32_t zero[K], nt[K], u[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) zero[k] = 0;
+      for (int prec = 32; prec < m; prec *= 2) {
+        w.mul_low(t, sN, sNI);                          // N inv mod R
+#pragma unroll
+        for (int k = 0; k < K; ++k) nt[k] = lane < nb ? ~t[k] : 0u;
+        add<K>(u, nt, zero, 3u, lane, nb);              // 2 - t = ~t + 3
+        w.store_block(sU, u);
+        __syncwarp();
+        w.mul_low(t, sNI, sU);
+        __syncwarp();
+        w.store_block(sNI, t);
+        __syncwarp();
+      }
+      w.load_block(t, sNI);
+#pragma unroll
+      for (int k = 0; k < K; ++k) nt[k] = lane < nb ? ~t[k] : 0u;
+      add<K>(x, nt, zero, 1u, lane, nb);                // negate
+      w.store_block(sNI, x);
+      __syncwarp();
+    }
+    // ---- R mod N: 2^(n-1) doubled m - n + 1 times with a conditional subtraction each
+    {
+      uint32_t nz = 0;
+      int top_bit = 0;   // bit length within this lane's block
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        nz |= nreg[k];
+        if (nreg[k]) top_bit = 32 * k + (32 - __clz(nreg[k]));
+      }
+      const uint32_t lanes_nz = __ballot_sync(kCoopFull, nz != 0);
+      const int top_lane = 31 - __clz(lanes_nz);
+      top_bit = __shfl_sync(kCoopFull, top_bit, top_lane);
+      const int nbits = top_lane * 32 * K + top_bit;
+      const int b = nbits - 1;
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = (nbits > 1 && lane == b / (32 * K) && k == (b % (32 * K)) / 32) ? (1u << (b % 32)) : 0u;
+      for (int i = 0; i < m - b; ++i) double_mod<K>(x, nreg, lane, nb);   // N == 1: stays 0
+      w.store_block(sONE, x);
+      // R^2 mod N: 2^o R by doublings, then e Montgomery squarings, m = 2^e * o
+      int e = 0, o = m;
+      while ((o & 1) == 0) { o >>= 1; ++e; }
+      for (int i = 0; i < o; ++i) double_mod<K>(x, nreg, lane, nb);
+      w.store_block(sR2, x);
+      __syncwarp();
+      for (int i = 0; i < e; ++i) montmul<K>(w, sR2, sR2, sR2, 0, 0);
+    }
+    // ---- exponentiation: fixed windows, every window multiplies
+    montmul<K>(w, sX, sX, sR2, 0, 0);                   // x R
+    const int tn = (1 << p.wbits) - 1;
+    copy(tab, X, Lc);
+    copy(Y, X, Lc);
+    __syncwarp();
+    for (int k = 1; k < tn; ++k) {
+      montmul<K>(w, sX, sX, sY, 0, 0);
+      copy(tab + (size_t)k * Lc, X, Lc);
+    }
+    __syncwarp();
+    const uint32_t* ex = p.exps + g * (unsigned long long)p.exp_limbs;
+    auto digit = [&](int tdig) -> uint32_t {
+      const int lowbit = p.wbits * (p.ndigits - 1 - tdig);
+      uint32_t v = 0;
+      for (int bb = 0; bb < p.wbits; ++bb) {
+        const int bit = lowbit + bb;
+        if (bit < 32 * p.exp_limbs && ((ex[bit / 32] >> (bit % 32)) & 1u)) v |= 1u << bb;
+      }
+      return v;
+    };
+    {
+      const uint32_t d0 = digit(0);
+      if (d0) copy(X, tab + (size_t)(d0 - 1) * Lc, Lc); else copy(X, ONE, Lc);
+      __syncwarp();
+    }
+    for (int td = 1; td < p.ndigits; ++td) {
+      for (int q = 0; q < p.wbits; ++q) montmul<K>(w, sX, sX, sX, 0, 0);
+      const uint32_t dg = digit(td);
+      if (dg) { copy(Y, tab + (size_t)(dg - 1) * Lc, Lc); __syncwarp(); montmul<K>(w, sX, sX, sY, 0, 0); }
+      else montmul<K>(w, sX, sX, sONE, 0, 0);
+    }
+    // ---- out of the Montgomery domain, canonical residue
+    {
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = (lane == 0 && k == 0) ? 1u : 0u;
+      w.store_block(sY, x);
+      __syncwarp();
+      montmul<K>(w, sX, sX, sY, 0, 0);
+      w.load_block(x, sX);
+      if (sub<K>(t, x, nreg, lane, nb)) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = t[k];
+      }
+      w.store_block(sX, x);
+      __syncwarp();
+    }
+    uint32_t* o = p.out + idx * (unsigned long long)p.limbs;
+    for (int l = lane; l < p.limbs; l += 32) o[l] = X[l];
+    __syncwarp();
+  }
+}
+
+}  // namespace dkg

@@ -1,0 +1,52 @@
+// Launch parameters of the cooperative (warp-per-operand) kernels, dkg_coop.cuh (shared by the
+// kernels and the host dispatch).
+#pragma once
+#include <stdint.h>
+
+namespace dkg {
+
+constexpr unsigned kCoopFull = 0xffffffffu;
+constexpr int kCoopMaxBlocks = 16;
+
+// Host-built lane plan of one product phase (dkg_engine.cu: make_coop_plan).
+struct CoopPlanTable {
+  uint8_t d[32], i0[32], i1[32];
+  int8_t partner[3][32];  // lanes whose partial sum this (primary) lane adds; -1 = none
+  int32_t rounds;         // max number of partners of any lane
+  int32_t ndiag;          // lanes 0..ndiag-1 are primaries
+};
+
+struct CoopNsqParams {
+  const uint32_t* pairs_in;   // [count][2][Lc] plain pairs (c mod N, (c div N) * R mod N), R = 2^(32 Lc)
+  uint32_t* pairs_out;        // [count][2][Lc] plain pairs of the result
+  uint8_t* status;            // [count] or null: 1 = base not invertible (negative exponent only)
+  unsigned long long count;
+  int nb;                     // blocks per component; Lc = nb * K
+  int negative;
+  // N | NI (-N^-1 mod R) | DNEG (-R mod N) | R2A | R2B | ONEA | ONEB | TWOA | TWOB | PLAIN1 | ZERO
+  const uint32_t* consts;
+  const uint32_t* ops;        // operation list of the context (see ModexpParams)
+  int nops, tab_entries, table_odd;
+  uint32_t* scratch;          // per-warp window table, (tab_entries + 1) * 2 * Lc words
+  unsigned long long scratch_per_warp;
+  unsigned int* counter;
+  CoopPlanTable full, low;
+};
+constexpr int kCoopNsqConsts = 11;
+
+struct CoopGroupedParams {
+  const uint32_t* moduli;   // [groups][limbs]
+  const uint32_t* exps;     // [groups][exp_limbs]
+  const uint32_t* bases;    // [groups * per_group][limbs], each below its modulus
+  uint32_t* out;
+  unsigned long long groups;
+  int per_group, limbs, exp_limbs;
+  int nb;
+  int wbits, ndigits;
+  uint32_t* scratch;        // per-warp window table, (2^wbits - 1) * Lc words
+  unsigned long long scratch_per_warp;
+  unsigned int* counter;
+  CoopPlanTable full, low;
+};
+
+}  // namespace dkg

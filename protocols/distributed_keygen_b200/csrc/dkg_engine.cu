@@ -19,6 +19,7 @@
 #include "dkg_biprime.cuh"
 #include "dkg_nsq_params_fwd.h"
 #include "dkg_nsq_io.cuh"
+#include "dkg_coop_params.h"
 
 namespace {
 
@@ -75,6 +76,10 @@ GroupedFn lookup_grouped_group0(int, int); GroupedFn lookup_grouped_group1(int, 
 GroupedFn lookup_grouped_group2(int, int); GroupedFn lookup_grouped_group3(int, int);
 GroupedFn lookup_grouped_group4(int, int); GroupedFn lookup_grouped_group5(int, int);
 void launch_group_setup(const GroupedParams& p, cudaStream_t stream);
+// dkg_coop.cu: the cooperative (warp-per-operand) latency kernels
+int coop_max_warps(int K);
+cudaError_t launch_coop_nsq(int K, const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
+cudaError_t launch_coop_grouped(int K, const CoopGroupedParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
 }  // namespace dkg
 namespace {
 
@@ -112,7 +117,24 @@ struct DeviceState {
   unsigned int* counter = nullptr;
   uint32_t* aux = nullptr;  // batched-inversion buffers
   size_t aux_words = 0;
-  std::mutex mu;            // serialises the synchronous host-buffer entry points on this device
+  cudaEvent_t last = nullptr;  // end of the latest launch sequence that used scratch / aux / counter
+  std::mutex mu;            // held while a launch sequence is enqueued (and, for host buffers, until it is done)
+};
+
+// All contexts of a device share its scratch areas and the work ticket.  Every launch sequence --
+// from the host-buffer entry points on the internal stream and from the *_device entry points on
+// the caller's stream alike -- is enqueued under the device mutex and ordered on the device after
+// the previous one (cudaStreamWaitEvent on `last`), so two streams or threads can never have
+// kernels of this library running against the same scratch at the same time.
+struct DeviceLease {
+  DeviceState* d;
+  cudaStream_t s;
+  std::unique_lock<std::mutex> lk;
+  DeviceLease(DeviceState* d_, cudaStream_t s_) : d(d_), s(s_), lk(d_->mu) {
+    cudaSetDevice(d->device);
+    cudaStreamWaitEvent(s, d->last, 0);
+  }
+  ~DeviceLease() { cudaEventRecord(d->last, s); }
 };
 std::mutex g_dev_mu;
 DeviceState g_devs[16];
@@ -129,6 +151,7 @@ int device_state(int device, DeviceState** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&d.counter, sizeof(unsigned int)));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.last, cudaEventDisableTiming));
     // batch buffers of the host-buffer entry points come from the stream-ordered pool and stay
     // cached there between calls (no cudaMalloc/cudaFree on the data path)
     cudaMemPool_t pool;
@@ -188,6 +211,76 @@ int ensure_aux(DeviceState* d, size_t words) {
 
 }  // namespace
 
+
+namespace {
+
+// Lane plan of one product phase of the cooperative kernels (transcription of make_plan in
+// tests/coop_model.py): diagonal d of an nb x nb block product has the tiles (i, d - i),
+// max(0, d - nb + 1) <= i <= min(d, nb - 1); lane d is its primary, spare lanes take further chunks
+// of the long diagonals so that no lane has more than `c` tiles, c minimal.
+dkg::CoopPlanTable make_coop_plan(int nb, int ndiag) {
+  dkg::CoopPlanTable t{};
+  for (int l = 0; l < 32; ++l) { t.d[l] = 0; t.i0[l] = 0; t.i1[l] = 0; t.partner[0][l] = t.partner[1][l] = t.partner[2][l] = -1; }
+  std::vector<int> lo(ndiag), hi(ndiag), len(ndiag), chunks(ndiag);
+  for (int d = 0; d < ndiag; ++d) {
+    lo[d] = std::max(0, d - nb + 1);
+    hi[d] = std::min(d, nb - 1) + 1;
+    len[d] = hi[d] - lo[d];
+  }
+  int c = 1;
+  for (;; ++c) {
+    int lanes = 0, most = 0;
+    for (int d = 0; d < ndiag; ++d) { const int k = (len[d] + c - 1) / c; lanes += k; most = std::max(most, k); }
+    if (lanes <= 32 && most <= 4) break;
+  }
+  int next = ndiag, rounds = 0;
+  for (int d = 0; d < ndiag; ++d) {
+    chunks[d] = (len[d] + c - 1) / c;
+    const int per = (len[d] + chunks[d] - 1) / chunks[d];
+    for (int k = 0; k < chunks[d]; ++k) {
+      const int a = lo[d] + k * per, b = std::min(lo[d] + (k + 1) * per, hi[d]);
+      const int lane = k == 0 ? d : next++;
+      t.d[lane] = (uint8_t)d; t.i0[lane] = (uint8_t)a; t.i1[lane] = (uint8_t)std::max(a, b);
+      if (k > 0) t.partner[k - 1][d] = (int8_t)lane;
+    }
+    rounds = std::max(rounds, chunks[d] - 1);
+  }
+  t.rounds = rounds;
+  t.ndiag = ndiag;
+  return t;
+}
+
+// block size / block count of the cooperative kernels for `limbs` limbs per number
+bool coop_shape(int limbs, int* K, int* nb) {
+  for (int k : {6, 12}) {
+    const int n = (limbs + k - 1) / k;
+    if (n <= dkg::kCoopMaxBlocks) { *K = k; *nb = n; return true; }
+  }
+  return false;
+}
+
+long env_long(const char* name, long dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atol(v) : dflt;
+}
+// Largest batch the cooperative kernels take (0 disables them): below it a warp per operand beats
+// waiting for a thread-per-operand wave (DESIGN.md section 2.10 has the measured crossover).
+// Process-wide settings, initialised from the environment once (DKG_COOP=0 disables,
+// DKG_COOP_MAX / DKG_COOP_GROUPED_MAX set the limits) and changed through dkg_config_set; a
+// fixed-modulus context takes its limit when it is created.
+std::atomic<long> g_coop_max{-1}, g_coop_grouped_max{-1};
+size_t coop_limit(std::atomic<long>& slot, const char* env_name, long dflt) {
+  long v = slot.load();
+  if (v < 0) {
+    v = env_long("DKG_COOP", 1) == 0 ? 0 : std::max(0L, env_long(env_name, dflt));
+    slot.store(v);
+  }
+  return (size_t)v;
+}
+constexpr long kCoopMaxDefault = 8192, kCoopGroupedMaxDefault = 16384;
+
+}  // namespace
+
 struct dkg_modexp_ctx {
   DeviceState* dev = nullptr;
   int limbs = 0;  // caller-visible row width
@@ -215,6 +308,15 @@ struct dkg_modexp_ctx {
   dkg::NsqFn nsq_kernel = nullptr;
   uint32_t* d_nconsts = nullptr;   // kernel constants
   uint32_t* d_nio = nullptr;       // entry/exit constants
+  // cooperative (warp-per-operand) latency path for small batches (dkg_coop.cuh): its own R = 2^(32 cLc)
+  bool coop = false;
+  int cK = 0, cnb = 0, cLc = 0;
+  size_t coop_max = 0;             // largest batch routed to it
+  uint32_t* d_cconsts = nullptr;   // kernel constants (CoopNsqParams::consts)
+  uint32_t* d_cio = nullptr;       // entry/exit constants for cLc
+  dkg::CoopPlanTable cfull{}, clow{};
+  bool use_nsq = true;             // knobs read once, when the context is created
+  bool use_batch_inverse = true;
 };
 
 namespace {
@@ -282,6 +384,8 @@ std::vector<uint32_t> sliding_window_ops(const uint32_t* e, int ebits, int w, in
 
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
                       size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows = nullptr, int m_limbs = 0);
+int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status, size_t count,
+                       cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs);
 
 // Chain warps of the batched inversion: chains of 32 groups keep the binary-GCD count at 1/32 of
 // the elements but leave most SMs idle (56 warps for a 56 832-element launch); the chain products
@@ -300,7 +404,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
-  if (ctx->nsq && d_final_mul == nullptr && !getenv("DKG_NO_NSQ")) {
+  if (ctx->nsq && d_final_mul == nullptr && ctx->use_nsq) {
     bool handled = false;
     int rc0 = launch_modexp_nsq(ctx, d_bases, d_out, d_status, count, stream, &handled);
     if (rc0 != DKG_OK || handled) return rc0;
@@ -313,7 +417,7 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::ModexpParams p{};
-  if (ctx->negative && ctx->inv_kernel != nullptr && ngroups >= 2 && !getenv("DKG_NO_BATCH_INVERSE")) {
+  if (ctx->negative && ctx->inv_kernel != nullptr && ngroups >= 2 && ctx->use_batch_inverse) {
     // Montgomery's trick along chains of ~32 groups: one binary-GCD inversion per chain lane
     const size_t gwords = (size_t)ctx->Lp * 32;
     const int nchain = inversion_chain_warps(d, ctx, ngroups);
@@ -342,6 +446,49 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
   return DKG_OK;
 }
 
+// Launch geometry of the cooperative kernels: one instance per warp; spread small batches over the
+// SMs first (one warp per CTA), then stack warps, then go persistent (work ticket).
+void coop_grid(const DeviceState* d, int K, size_t count, int* ctas, int* warps) {
+  const int maxw = dkg::coop_max_warps(K);
+  if (count <= (size_t)d->sm_count) { *warps = 1; *ctas = (int)count; return; }
+  *warps = (int)std::min<size_t>(maxw, (count + d->sm_count - 1) / d->sm_count);
+  *ctas = (int)std::min<size_t>((count + *warps - 1) / *warps, (size_t)d->sm_count * std::max(1, maxw / *warps));
+}
+
+// Small batches modulo N^2: entry -> cooperative pair exponentiation (a warp per ciphertext,
+// negative exponents inverted in the kernel, per-element status) -> exit.
+int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status, size_t count,
+                       cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs) {
+  DeviceState* d = ctx->dev;
+  const int Lc = ctx->cLc;
+  int ctas = 1, warps = 1;
+  coop_grid(d, ctx->cK, count, &ctas, &warps);
+  const size_t per_warp = ((size_t)ctx->tab_entries + 1) * 2 * Lc;
+  const size_t pair_words = count * (size_t)(2 * Lc);
+  int rc = ensure_scratch(d, (size_t)ctas * warps * per_warp);
+  if (rc == DKG_OK) rc = ensure_aux(d, pair_words);
+  if (rc != DKG_OK) return rc;
+  uint32_t* pairs = d->aux;
+  dkg::NsqIoParams e{};
+  e.in = d_bases; e.out = pairs; e.count = count; e.io_limbs = ctx->limbs; e.Lp = Lc; e.consts = ctx->d_cio; e.n0inv = ctx->n_n0inv;
+  e.mrows = nullptr; e.m_limbs = 0;
+  dkg::nsq_entry_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(e);
+  CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
+  dkg::CoopNsqParams q{};
+  q.pairs_in = pairs; q.pairs_out = pairs; q.status = d_status; q.count = count; q.nb = ctx->cnb; q.negative = ctx->negative;
+  q.consts = ctx->d_cconsts; q.ops = ctx->d_ops; q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd;
+  q.scratch = d->scratch; q.scratch_per_warp = per_warp; q.counter = d->counter; q.full = ctx->cfull; q.low = ctx->clow;
+  const size_t smem = ((size_t)dkg::kCoopNsqConsts + (size_t)12 * warps) * Lc * 4;
+  CUDA_TRY(dkg::launch_coop_nsq(ctx->cK, q, ctas, warps, smem, stream));
+  dkg::NsqIoParams x = e;
+  x.in = pairs; x.out = d_out; x.mrows = d_mrows; x.m_limbs = m_limbs;
+  dkg::nsq_exit_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(x);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(3);
+  *handled = true;
+  return DKG_OK;
+}
+
 // Modulus N^2 with known N: [batched inversion ->] entry (pairs) -> pair exponentiation -> exit.
 // Falls back to the direct kernel (handled = false) when a chain of the batched inversion hit a
 // non-unit, so that the per-element status comes out exact.
@@ -349,6 +496,7 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
                       size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs) {
   DeviceState* d = ctx->dev;
   *handled = false;
+  if (ctx->coop && count <= ctx->coop_max) return launch_modexp_coop(ctx, d_bases, d_out, d_status, count, stream, handled, d_mrows, m_limbs);
   const unsigned long long ngroups = (count + 31) / 32;
   const int Lp = ctx->nLp;
   const size_t pair_words = count * (size_t)(2 * Lp);
@@ -443,6 +591,21 @@ int dkg_device_count(int* count) {
 
 unsigned long long dkg_launch_count(void) { return g_launches.load(); }
 
+int dkg_config_set(const char* key, long value) {
+  if (!key || value < 0) return fail(DKG_ERR_INVALID, "bad configuration key/value");
+  const std::string k(key);
+  if (k == "coop_max") { coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault); g_coop_max.store(value); return DKG_OK; }
+  if (k == "coop_grouped_max") { g_coop_grouped_max.store(value); return DKG_OK; }
+  return fail(DKG_ERR_INVALID, "unknown configuration key");
+}
+int dkg_config_get(const char* key, long* value) {
+  if (!key || !value) return fail(DKG_ERR_INVALID, "null argument");
+  const std::string k(key);
+  if (k == "coop_max") { *value = (long)coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault); return DKG_OK; }
+  if (k == "coop_grouped_max") { *value = (long)coop_limit(g_coop_grouped_max, "DKG_COOP_GROUPED_MAX", kCoopGroupedMaxDefault); return DKG_OK; }
+  return fail(DKG_ERR_INVALID, "unknown configuration key");
+}
+
 int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, const uint32_t* exponent,
                           int exp_limbs, int exp_negative, dkg_modexp_ctx** out) {
   if (!modulus || !out || mod_limbs <= 0 || exp_limbs < 0 || (exp_limbs > 0 && !exponent))
@@ -462,6 +625,8 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   ctx->shape = shape;
   ctx->Lp = shape.K * shape.M;
   ctx->negative = exp_negative ? 1 : 0;
+  ctx->use_nsq = getenv("DKG_NO_NSQ") == nullptr;   // environment knobs are read here, once per context
+  ctx->use_batch_inverse = getenv("DKG_NO_BATCH_INVERSE") == nullptr;
   ctx->kernel = lookup_kernel(shape.K, shape.M);
   if (!ctx->kernel) { delete ctx; return fail(DKG_ERR_UNSUPPORTED, "kernel shape not compiled"); }
 
@@ -557,6 +722,8 @@ void dkg_modexp_ctx_destroy(dkg_modexp_ctx* ctx) {
   if (ctx->d_ops) cudaFree(ctx->d_ops);
   if (ctx->d_nconsts) cudaFree(ctx->d_nconsts);
   if (ctx->d_nio) cudaFree(ctx->d_nio);
+  if (ctx->d_cconsts) cudaFree(ctx->d_cconsts);
+  if (ctx->d_cio) cudaFree(ctx->d_cio);
   delete ctx;
 }
 
@@ -661,6 +828,70 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
   }
   ctx->nshape = sh; ctx->nLp = Lp; ctx->nwarps = warps; ctx->nsmem = uni + per_warp * warps;
   ctx->n_n0inv = ninv[0]; ctx->nsq_kernel = kernel; ctx->nsq = true;
+
+  // ---- cooperative (warp-per-operand) latency path, dkg_coop.cuh: its own R = 2^(32 cLc) >= 8N -----
+  int cK = 0, cnb = 0;
+  const size_t coop_max = coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault);
+  if (coop_max > 0 && coop_shape(need, &cK, &cnb) && cK * cnb <= dkg::kNsqMaxL) {
+    const int Lc = cK * cnb;
+    dkg_host::Limbs Nc(Lc, 0);
+    for (int i = 0; i < ln; ++i) Nc[i] = nn[i];
+    dkg_host::Limbs ni_c = dkg_host::neg_inv_block(Nc, Lc);
+    dkg_host::Limbs ninvpos_c(Lc);
+    {
+      uint64_t carry = 1;
+      for (int i = 0; i < Lc; ++i) { uint64_t t = (uint64_t)(~ni_c[i]) + carry; ninvpos_c[i] = (uint32_t)t; carry = t >> 32; }
+    }
+    dkg_host::Limbs r_c = dkg_host::pow2_mod((size_t)32 * Lc, Nc), r2_c = dkg_host::pow2_mod((size_t)64 * Lc, Nc);
+    dkg_host::Limbs dneg_c(Lc, 0);
+    {
+      bool zero_r = true;
+      for (uint32_t w : r_c) zero_r = zero_r && (w == 0);
+      if (!zero_r) { dneg_c = Nc; dkg_host::sub_inplace(dneg_c, r_c); }
+    }
+    auto plain_pair_c = [&](size_t pow2bits, dkg_host::Limbs* pa, dkg_host::Limbs* pb) {
+      dkg_host::Limbs g = dkg_host::pow2_mod(pow2bits, n2p);
+      dkg_host::Limbs nshort(nn.begin(), nn.begin() + ln), qd, rd;
+      dkg_host::divmod_slow(g, nshort, &qd, &rd);
+      pa->assign(Lc, 0);
+      for (int i = 0; i < ln; ++i) (*pa)[i] = rd[i];
+      dkg_host::Limbs g1(Lc, 0);
+      for (int i = 0; i < (int)qd.size() && i < Lc; ++i) g1[i] = qd[i];
+      *pb = dkg_host::mulmod_slow(g1, r_c, Nc);
+    };
+    dkg_host::Limbs cr2a, cr2b, conea, coneb;
+    plain_pair_c((size_t)64 * Lc, &cr2a, &cr2b);
+    plain_pair_c((size_t)32 * Lc, &conea, &coneb);
+    // constants of the Newton step of the in-kernel inversion: 2*ONE as (2 a + 2N, 2 b - 2R mod N)
+    dkg_host::Limbs twoa(Lc, 0), twob;
+    {
+      uint64_t carry = 0;
+      for (int i = 0; i < Lc; ++i) { uint64_t t = (uint64_t)conea[i] + Nc[i] + carry; twoa[i] = (uint32_t)t; carry = t >> 32; }
+      uint32_t c2 = 0;
+      for (int i = 0; i < Lc; ++i) { const uint32_t nc = twoa[i] >> 31; twoa[i] = (twoa[i] << 1) | c2; c2 = nc; }
+      const dkg_host::Limbs b2 = dkg_host::addmod(coneb, coneb, Nc), rr = dkg_host::addmod(r_c, r_c, Nc);
+      twob = dkg_host::submod(b2, rr, Nc);
+    }
+    dkg_host::Limbs cplain1(Lc, 0), czero(Lc, 0);
+    cplain1[0] = 1;
+    std::vector<uint32_t> cc, cio;
+    for (const dkg_host::Limbs* v : {&Nc, &ni_c, &dneg_c, &cr2a, &cr2b, &conea, &coneb, &twoa, &twob, &cplain1, &czero})
+      cc.insert(cc.end(), v->begin(), v->end());
+    for (const dkg_host::Limbs* v : {&Nc, &r2_c, &ninvpos_c}) cio.insert(cio.end(), v->begin(), v->end());
+    cudaError_t e2 = cudaMalloc(&ctx->d_cconsts, cc.size() * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->d_cio, cio.size() * 4);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->d_cconsts, cc.data(), cc.size() * 4, cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->d_cio, cio.data(), cio.size() * 4, cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) {
+      dkg_modexp_ctx_destroy(ctx);
+      *out = nullptr;
+      return fail(DKG_ERR_CUDA, std::string("cooperative-path constants: ") + cudaGetErrorString(e2));
+    }
+    ctx->cK = cK; ctx->cnb = cnb; ctx->cLc = Lc; ctx->coop_max = coop_max;
+    ctx->cfull = make_coop_plan(cnb, 2 * cnb - 1);
+    ctx->clow = make_coop_plan(cnb, cnb);
+    ctx->coop = true;
+  }
   return DKG_OK;
 }
 
@@ -675,6 +906,7 @@ int dkg_modexp_ctx_info(const dkg_modexp_ctx* ctx, int info[12]) {
 int dkg_modexp_batch_device(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
                             uint8_t* d_status, size_t count, void* stream) {
   if (!ctx || (count && (!d_bases || !d_out))) return fail(DKG_ERR_INVALID, "null argument");
+  DeviceLease lease(ctx->dev, (cudaStream_t)stream);
   return launch_modexp(ctx, d_bases, d_out, d_status, nullptr, count, (cudaStream_t)stream);
 }
 
@@ -684,7 +916,7 @@ int dkg_modexp_batch(dkg_modexp_ctx* ctx, const uint32_t* bases, uint32_t* out, 
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
-  std::lock_guard<std::mutex> lk(d->mu);
+  DeviceLease lease(d, d->stream);
   DevBufs bufs(d->stream);
   const size_t bytes = count * (size_t)ctx->limbs * 4;
   uint32_t *d_in, *d_out;
@@ -799,6 +1031,7 @@ int dkg_combine_n2_limbs(const dkg_combine_ctx* ctx) { return ctx ? ctx->l2 : 0;
 int dkg_combine_batch_device(dkg_combine_ctx* ctx, const uint32_t* d_partials, uint32_t* d_out, uint8_t* d_status,
                              size_t count, void* stream) {
   if (!ctx || (count && (!d_partials || !d_out))) return fail(DKG_ERR_INVALID, "null argument");
+  DeviceLease lease(ctx->dev, (cudaStream_t)stream);
   return launch_combine(ctx, d_partials, d_out, d_status, count, (cudaStream_t)stream);
 }
 
@@ -807,7 +1040,7 @@ int dkg_combine_batch(dkg_combine_ctx* ctx, const uint32_t* partials, uint32_t* 
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
-  std::lock_guard<std::mutex> lk(d->mu);
+  DeviceLease lease(d, d->stream);
   DevBufs bufs(d->stream);
   const size_t in_bytes = (size_t)ctx->shares * count * ctx->l2 * 4, out_bytes = count * (size_t)ctx->ln * 4;
   uint32_t *d_in, *d_out;
@@ -837,7 +1070,7 @@ extern "C" int dkg_encrypt_batch(dkg_modexp_ctx* ctx, const uint32_t* n, int n_l
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
   const size_t in_bytes = count * (size_t)n_limbs * 4, out_bytes = count * (size_t)ctx->limbs * 4;
-  std::lock_guard<std::mutex> lk(d->mu);
+  DeviceLease lease(d, d->stream);
   DevBufs bufs(d->stream);
   uint32_t *d_r, *d_m = nullptr, *d_n, *d_base, *d_fm = nullptr, *d_out;
   cudaError_t e = bufs.alloc(&d_r, in_bytes);
@@ -860,7 +1093,7 @@ extern "C" int dkg_encrypt_batch(dkg_modexp_ctx* ctx, const uint32_t* n, int n_l
   CUDA_TRY(cudaGetLastError());
   int rc = DKG_OK;
   bool handled = false;
-  if (ctx->nsq && !getenv("DKG_NO_NSQ"))  // r^N in pair arithmetic, (1 + m N) folded into the exit step
+  if (ctx->nsq && ctx->use_nsq)  // r^N in pair arithmetic, (1 + m N) folded into the exit step
     rc = launch_modexp_nsq(ctx, d_base, d_out, nullptr, count, d->stream, &handled, m ? d_m : nullptr, n_limbs);
   if (rc == DKG_OK && !handled) rc = launch_modexp(ctx, d_base, d_out, nullptr, m ? d_fm : nullptr, count, d->stream);
   if (rc != DKG_OK) return rc;
@@ -930,6 +1163,47 @@ int plan_grouped(DeviceState* d, int limbs, int ebits, size_t count, GroupedPlan
   return DKG_OK;
 }
 
+// Cooperative (warp-per-operand) variant for small candidate batches, dkg_coop.cuh: needs no
+// per-group constants (each warp derives -N^-1, R, R^2 for its instance) and no setup kernel.
+struct CoopGroupedPlan {
+  int K = 0, nb = 0, Lc = 0, wbits = 1, ndigits = 1, ctas = 1, warps = 1;
+  size_t smem = 0, per_warp = 0;
+  dkg::CoopPlanTable full{}, low{};
+};
+
+// true if this batch should take the cooperative kernel (moduli: host copy, for the widest one)
+bool plan_coop_grouped(DeviceState* d, const uint32_t* moduli, size_t groups, int limbs, int ebits, size_t count,
+                       CoopGroupedPlan* plan) {
+  if (count == 0 || count > coop_limit(g_coop_grouped_max, "DKG_COOP_GROUPED_MAX", kCoopGroupedMaxDefault)) return false;
+  int maxbits = 1;
+  for (size_t g = 0; g < groups; ++g) maxbits = std::max(maxbits, dkg_host::bit_length(moduli + g * (size_t)limbs, limbs));
+  const int need = (maxbits + 2 + 31) / 32;   // R >= 4N
+  if (!coop_shape(need, &plan->K, &plan->nb)) return false;
+  plan->Lc = plan->K * plan->nb;
+  plan->wbits = choose_window(ebits);
+  plan->ndigits = std::max(1, (ebits + plan->wbits - 1) / plan->wbits);
+  coop_grid(d, plan->K, count, &plan->ctas, &plan->warps);
+  plan->smem = (size_t)9 * plan->warps * plan->Lc * 4;
+  plan->per_warp = (((size_t)1 << plan->wbits) - 1) * plan->Lc;
+  plan->full = make_coop_plan(plan->nb, 2 * plan->nb - 1);
+  plan->low = make_coop_plan(plan->nb, plan->nb);
+  return true;
+}
+
+int launch_coop_grouped_batch(DeviceState* d, const CoopGroupedPlan& plan, const uint32_t* d_mod, const uint32_t* d_exp,
+                              int exp_limbs, const uint32_t* d_bases, uint32_t* d_out, size_t groups, int per_group, int limbs) {
+  int rc = ensure_scratch(d, (size_t)plan.ctas * plan.warps * plan.per_warp);
+  if (rc != DKG_OK) return rc;
+  CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), d->stream));
+  dkg::CoopGroupedParams p{};
+  p.moduli = d_mod; p.exps = d_exp; p.bases = d_bases; p.out = d_out; p.groups = groups; p.per_group = per_group;
+  p.limbs = limbs; p.exp_limbs = exp_limbs; p.nb = plan.nb; p.wbits = plan.wbits; p.ndigits = plan.ndigits;
+  p.scratch = d->scratch; p.scratch_per_warp = plan.per_warp; p.counter = d->counter; p.full = plan.full; p.low = plan.low;
+  CUDA_TRY(dkg::launch_coop_grouped(plan.K, p, plan.ctas, plan.warps, plan.smem, d->stream));
+  g_launches.fetch_add(1);
+  return DKG_OK;
+}
+
 // enqueue setup + grouped modexp on device buffers (gconsts/digits are caller-allocated scratch)
 int launch_grouped(DeviceState* d, const GroupedPlan& plan, const uint32_t* d_mod, const uint32_t* d_exp, int exp_limbs,
                    const uint32_t* d_bases, uint32_t* d_out, size_t groups, int per_group, int limbs,
@@ -964,25 +1238,30 @@ extern "C" int dkg_modexp_grouped(int device, const uint32_t* moduli, const uint
   int ebits = 0;
   for (size_t g = 0; g < groups; ++g) ebits = std::max(ebits, dkg_host::bit_length(exps + g * (size_t)exp_limbs, exp_limbs));
   const size_t count = groups * (size_t)per_group;
+  DeviceLease lease(d, d->stream);
+  CoopGroupedPlan cplan;
+  const bool coop = plan_coop_grouped(d, moduli, groups, limbs, ebits, count, &cplan);
   GroupedPlan plan;
-  rc = plan_grouped(d, limbs, ebits, count, &plan);
-  if (rc != DKG_OK) return rc;
-  std::lock_guard<std::mutex> lk(d->mu);
+  if (!coop) {
+    rc = plan_grouped(d, limbs, ebits, count, &plan);
+    if (rc != DKG_OK) return rc;
+  }
   DevBufs bufs(d->stream);
-  uint32_t *d_mod, *d_exp, *d_bases, *d_out, *d_gc;
-  uint8_t* d_dig;
+  uint32_t *d_mod, *d_exp, *d_bases, *d_out, *d_gc = nullptr;
+  uint8_t* d_dig = nullptr;
   const size_t mod_b = groups * (size_t)limbs * 4, exp_b = groups * (size_t)exp_limbs * 4, base_b = count * (size_t)limbs * 4;
   cudaError_t e = bufs.alloc(&d_mod, mod_b);
   if (e == cudaSuccess) e = bufs.alloc(&d_exp, exp_b);
   if (e == cudaSuccess) e = bufs.alloc(&d_bases, base_b);
   if (e == cudaSuccess) e = bufs.alloc(&d_out, base_b);
-  if (e == cudaSuccess) e = bufs.alloc(&d_gc, groups * (size_t)(3 * plan.Lp + plan.K) * 4);
-  if (e == cudaSuccess) e = bufs.alloc(&d_dig, groups * (size_t)plan.ndigits);
+  if (e == cudaSuccess && !coop) e = bufs.alloc(&d_gc, groups * (size_t)(3 * plan.Lp + plan.K) * 4);
+  if (e == cudaSuccess && !coop) e = bufs.alloc(&d_dig, groups * (size_t)plan.ndigits);
   if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("grouped cudaMalloc: ") + cudaGetErrorString(e));
   CUDA_TRY(cudaMemcpyAsync(d_mod, moduli, mod_b, cudaMemcpyHostToDevice, d->stream));
   CUDA_TRY(cudaMemcpyAsync(d_exp, exps, exp_b, cudaMemcpyHostToDevice, d->stream));
   CUDA_TRY(cudaMemcpyAsync(d_bases, bases, base_b, cudaMemcpyHostToDevice, d->stream));
-  rc = launch_grouped(d, plan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, per_group, limbs, d_gc, d_dig);
+  rc = coop ? launch_coop_grouped_batch(d, cplan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, per_group, limbs)
+            : launch_grouped(d, plan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, per_group, limbs, d_gc, d_dig);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(out, d_out, base_b, cudaMemcpyDeviceToHost, d->stream));
   CUDA_TRY(cudaStreamSynchronize(d->stream));
@@ -1007,13 +1286,17 @@ extern "C" int dkg_biprime_v_batch(int device, const uint32_t* moduli, const uin
   int ebits = 0;
   for (size_t g = 0; g < groups; ++g) ebits = std::max(ebits, dkg_host::bit_length(exps + g * (size_t)exp_limbs, exp_limbs));
   const size_t count = groups * (size_t)correct;
+  DeviceLease lease(d, d->stream);
+  CoopGroupedPlan cplan;
+  const bool coop = plan_coop_grouped(d, moduli, groups, limbs, ebits, count, &cplan);
   GroupedPlan plan;
-  rc = plan_grouped(d, limbs, ebits, count, &plan);
-  if (rc != DKG_OK) return rc;
-  std::lock_guard<std::mutex> lk(d->mu);
+  if (!coop) {
+    rc = plan_grouped(d, limbs, ebits, count, &plan);
+    if (rc != DKG_OK) return rc;
+  }
   DevBufs bufs(d->stream);
-  uint32_t *d_mod, *d_exp, *d_g, *d_bases, *d_out, *d_gc;
-  uint8_t* d_dig;
+  uint32_t *d_mod, *d_exp, *d_g, *d_bases, *d_out, *d_gc = nullptr;
+  uint8_t* d_dig = nullptr;
   int8_t* d_sym;
   int *d_pick, *d_count;
   const size_t mod_b = groups * (size_t)limbs * 4, exp_b = groups * (size_t)exp_limbs * 4;
@@ -1023,8 +1306,8 @@ extern "C" int dkg_biprime_v_batch(int device, const uint32_t* moduli, const uin
   if (e == cudaSuccess) e = bufs.alloc(&d_g, g_b);
   if (e == cudaSuccess) e = bufs.alloc(&d_bases, base_b);
   if (e == cudaSuccess) e = bufs.alloc(&d_out, base_b);
-  if (e == cudaSuccess) e = bufs.alloc(&d_gc, groups * (size_t)(3 * plan.Lp + plan.K) * 4);
-  if (e == cudaSuccess) e = bufs.alloc(&d_dig, groups * (size_t)plan.ndigits);
+  if (e == cudaSuccess && !coop) e = bufs.alloc(&d_gc, groups * (size_t)(3 * plan.Lp + plan.K) * 4);
+  if (e == cudaSuccess && !coop) e = bufs.alloc(&d_dig, groups * (size_t)plan.ndigits);
   if (e == cudaSuccess) e = bufs.alloc(&d_sym, groups * (size_t)g_per_candidate);
   if (e == cudaSuccess) e = bufs.alloc(&d_pick, count * sizeof(int));
   if (e == cudaSuccess) e = bufs.alloc(&d_count, groups * sizeof(int));
@@ -1039,7 +1322,8 @@ extern "C" int dkg_biprime_v_batch(int device, const uint32_t* moduli, const uin
   dkg::gather_g_kernel<<<gblocks, 256, 0, d->stream>>>(d_g, d_pick, limbs, groups, g_per_candidate, correct, d_bases);
   g_launches.fetch_add(3);
   CUDA_TRY(cudaGetLastError());
-  rc = launch_grouped(d, plan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, correct, limbs, d_gc, d_dig);
+  rc = coop ? launch_coop_grouped_batch(d, cplan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, correct, limbs)
+            : launch_grouped(d, plan, d_mod, d_exp, exp_limbs, d_bases, d_out, groups, correct, limbs, d_gc, d_dig);
   if (rc != DKG_OK) return rc;
   dkg::clear_unused_kernel<<<gblocks, 256, 0, d->stream>>>(d_out, d_count, limbs, groups, correct);
   g_launches.fetch_add(1);
@@ -1062,7 +1346,7 @@ extern "C" int dkg_jacobi_batch(int device, const uint32_t* moduli, const uint32
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  std::lock_guard<std::mutex> lk(d->mu);
+  DeviceLease lease(d, d->stream);
   DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_g;
   int8_t* d_sym;
@@ -1093,7 +1377,7 @@ extern "C" int dkg_small_prime_sieve(int device, const uint32_t* moduli, const u
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  std::lock_guard<std::mutex> lk(d->mu);
+  DeviceLease lease(d, d->stream);
   DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_pr;
   uint8_t* d_fl;
@@ -1127,7 +1411,7 @@ extern "C" int dkg_biprime_verdict(int device, const uint32_t* moduli, const uin
   int rc = device_state(device, &d);
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaSetDevice(device));
-  std::lock_guard<std::mutex> lk(d->mu);
+  DeviceLease lease(d, d->stream);
   DevBufs bufs(d->stream);
   uint32_t *d_mod, *d_v, *d_ok;
   const size_t mod_b = groups * (size_t)limbs * 4, v_b = (size_t)parties * groups * correct * limbs * 4;

@@ -85,6 +85,32 @@ inline Limbs neg_inv_block(const Limbs& n, int K) {
   return inv;
 }
 
+// (a + b) mod n and (a - b) mod n for a, b < n (same length)
+inline Limbs addmod(const Limbs& a, const Limbs& b, const Limbs& n) {
+  Limbs r(a.size());
+  uint64_t c = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    uint64_t t = (uint64_t)a[i] + b[i] + c;
+    r[i] = (uint32_t)t;
+    c = t >> 32;
+  }
+  if (c || geq(r, n)) sub_inplace(r, n);
+  return r;
+}
+inline Limbs submod(const Limbs& a, const Limbs& b, const Limbs& n) {
+  Limbs r = a;
+  if (!geq(a, b)) {
+    uint64_t c = 0;
+    for (size_t i = 0; i < r.size(); ++i) {
+      uint64_t t = (uint64_t)r[i] + n[i] + c;
+      r[i] = (uint32_t)t;
+      c = t >> 32;
+    }
+  }
+  sub_inplace(r, b);
+  return r;
+}
+
 // a * b mod n by shift-and-add (only used for tiny one-off constants)
 inline Limbs mulmod_slow(const Limbs& a, const Limbs& b, const Limbs& n) {
   const size_t len = n.size();
