@@ -3,8 +3,10 @@
 
 namespace dkg {
 
-// K = 6: up to 96 limbs per component, 16 warps per CTA; K = 12: up to 192 limbs, 8 warps.
-int coop_max_warps(int K) { return K == 6 ? 16 : 8; }
+// K = 6: up to 96 limbs per number; K = 12: up to 192.  Warps per CTA: the pair kernel runs two
+// interleaved products per warp and wants the registers of a 256-thread CTA; the grouped kernel at
+// K = 6 fits 16 warps.
+int coop_max_warps(int K, bool pair_kernel) { return (K == 6 && !pair_kernel) ? 16 : 8; }
 
 template <int K, int THREADS>
 static cudaError_t launch_nsq_t(const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
@@ -24,7 +26,7 @@ static cudaError_t launch_grouped_t(const CoopGroupedParams& p, int ctas, int wa
 }
 
 cudaError_t launch_coop_nsq(int K, const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
-  if (K == 6) return launch_nsq_t<6, 512>(p, ctas, warps, smem, stream);
+  if (K == 6) return launch_nsq_t<6, 256>(p, ctas, warps, smem, stream);
   if (K == 12) return launch_nsq_t<12, 256>(p, ctas, warps, smem, stream);
   return cudaErrorInvalidValue;
 }

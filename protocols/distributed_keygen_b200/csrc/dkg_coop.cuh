@@ -82,49 +82,73 @@ struct LanePlan {
   }
 };
 
-// E_d on the primary lanes (2K+2 limbs), zero elsewhere.  X, Y (and the optional second pair, X2 != 0)
-// are nb-block numbers in shared memory.
-template <int K>
-__device__ __forceinline__ void product(uint32_t (&e)[2 * K + 2], const LanePlan& lp, int lane, sa X, sa Y, sa X2, sa Y2) {
-  ColAcc<K> a;
+// E_d on the primary lanes (2K+2 limbs), zero elsewhere, for NS independent products at once.  X, Y
+// (and the optional second pair of a stream, X2 != 0) are nb-block numbers in shared memory.  The
+// streams share the lane plan; their block products and carry chains are independent, so ptxas
+// interleaves them and one warp hides its own latencies (a single chain issues one dependent
+// instruction every ~4.6 cycles).
+template <int K, int NS>
+__device__ __forceinline__ void product(uint32_t (&e)[NS][2 * K + 2], const LanePlan& lp, int lane, const sa (&X)[NS],
+                                        const sa (&Y)[NS], const sa (&X2)[NS], const sa (&Y2)[NS]) {
+  ColAcc<K> a[NS];
 #pragma unroll
-  for (int p = 0; p < 2 * K + 2; ++p) e[p] = 0;
-  acc_load<K>(a, e);
-  acc_clear_side<K>(a);
+  for (int s = 0; s < NS; ++s) {
+#pragma unroll
+    for (int p = 0; p < 2 * K + 2; ++p) e[s][p] = 0;
+    acc_load<K>(a[s], e[s]);
+    acc_clear_side<K>(a[s]);
+  }
   const NoIO<K> io;
   const typename NoIO<K>::Prefetch pf;
   for (int i = lp.i0; i < lp.i1; ++i) {
-    uint32_t xb[K], yb[K];
-    lds<K>(xb, X + (uint32_t)(i * K * 4));
-    lds<K>(yb, Y + (uint32_t)((lp.d - i) * K * 4));
-    block_mac<K>(a, xb, yb, io, pf);
-    if (X2 != 0) {
-      lds<K>(xb, X2 + (uint32_t)(i * K * 4));
-      lds<K>(yb, Y2 + (uint32_t)((lp.d - i) * K * 4));
-      block_mac<K>(a, xb, yb, io, pf);
+    uint32_t xb[NS][K], yb[NS][K];
+    const uint32_t ox = (uint32_t)(i * K * 4), oy = (uint32_t)((lp.d - i) * K * 4);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { lds<K>(xb[s], X[s] + ox); lds<K>(yb[s], Y[s] + oy); }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) block_mac<K>(a[s], xb[s], yb[s], io, pf);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (X2[s] != 0) {
+        lds<K>(xb[s], X2[s] + ox);
+        lds<K>(yb[s], Y2[s] + oy);
+        block_mac<K>(a[s], xb[s], yb[s], io, pf);
+      }
     }
   }
   __syncwarp();
-  acc_merge<K>(a, e);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc_merge<K>(a[s], e[s]);
   for (int r = 0; r < lp.rounds; ++r) {
     const int src = r == 0 ? lp.p0 : (r == 1 ? lp.p1 : lp.p2);
     const int from = src >= 0 ? src : lane;
     const uint32_t m = src >= 0 ? 0xffffffffu : 0u;
-    uint32_t t[2 * K + 2];
 #pragma unroll
-    for (int k = 0; k < 2 * K + 2; ++k) t[k] = __shfl_sync(kCoopFull, e[k], from) & m;
-    uint32_t carry = 0;
+    for (int s = 0; s < NS; ++s) {
+      uint32_t t[2 * K + 2];
 #pragma unroll
-    for (int k = 0; k < 2 * K + 2; ++k) {
-      const uint64_t s = (uint64_t)e[k] + t[k] + carry;
-      e[k] = (uint32_t)s;
-      carry = (uint32_t)(s >> 32);
+      for (int k = 0; k < 2 * K + 2; ++k) t[k] = __shfl_sync(kCoopFull, e[s][k], from) & m;
+      add_cc(e[s][0], t[0]);
+#pragma unroll
+      for (int k = 1; k < 2 * K + 1; ++k) addc_cc(e[s][k], t[k]);
+      addc(e[s][2 * K + 1], t[2 * K + 1]);
     }
   }
   if (lane >= lp.ndiag) {
 #pragma unroll
-    for (int k = 0; k < 2 * K + 2; ++k) e[k] = 0;
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+      for (int k = 0; k < 2 * K + 2; ++k) e[s][k] = 0;
+    }
   }
+}
+template <int K>
+__device__ __forceinline__ void product(uint32_t (&e)[2 * K + 2], const LanePlan& lp, int lane, sa X, sa Y, sa X2, sa Y2) {
+  uint32_t ee[1][2 * K + 2];
+  const sa x[1] = {X}, y[1] = {Y}, x2[1] = {X2}, y2[1] = {Y2};
+  product<K, 1>(ee, lp, lane, x, y, x2, y2);
+#pragma unroll
+  for (int k = 0; k < 2 * K + 2; ++k) e[k] = ee[0][k];
 }
 
 // carry into every lane from generate / propagate masks; bit 32+ = carry out of lane 31
@@ -146,57 +170,39 @@ __device__ __forceinline__ void resolve(uint32_t (&s)[K], const uint32_t (&e)[2 
   uint32_t h0 = __shfl_up_sync(kCoopFull, e[2 * K], 2), h1 = __shfl_up_sync(kCoopFull, e[2 * K + 1], 2);
   if (lane < 2) { h0 = 0; h1 = 0; }
   uint32_t c = 0;
-  {
-    uint32_t carry = 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const uint64_t t = (uint64_t)e[k] + mid[k] + carry;
-      s[k] = (uint32_t)t;
-      carry = (uint32_t)(t >> 32);
-    }
-    c += carry;
-    carry = 0;
+  for (int k = 0; k < K; ++k) s[k] = e[k];
+  add_cc(s[0], mid[0]);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const uint64_t t = (uint64_t)s[k] + (k == 0 ? h0 : (k == 1 ? h1 : 0u)) + carry;
-      s[k] = (uint32_t)t;
-      carry = (uint32_t)(t >> 32);
-    }
-    c += carry;
-    if (addend != nullptr) {
-      carry = 0;
+  for (int k = 1; k < K; ++k) addc_cc(s[k], mid[k]);
+  addc(c, 0);
+  add_cc(s[0], h0);
+  addc_cc(s[1], h1);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const uint64_t t = (uint64_t)s[k] + addend[k] + carry;
-        s[k] = (uint32_t)t;
-        carry = (uint32_t)(t >> 32);
-      }
-      c += carry;
-    }
+  for (int k = 2; k < K; ++k) addc_cc(s[k], 0);
+  addc(c, 0);
+  if (addend != nullptr) {
+    add_cc(s[0], addend[0]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) addc_cc(s[k], addend[k]);
+    addc(c, 0);
   }
   uint32_t cin = __shfl_up_sync(kCoopFull, c, 1);
   if (lane < 1) cin = 0;
   uint32_t g = 0, ones = 0xffffffffu;
-  {
-    uint32_t carry = cin;
+  add_cc(s[0], cin);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const uint64_t t = (uint64_t)s[k] + carry;
-      s[k] = (uint32_t)t;
-      carry = (uint32_t)(t >> 32);
-      ones &= s[k];
-    }
-    g = carry;
-  }
+  for (int k = 1; k < K; ++k) addc_cc(s[k], 0);
+  addc(g, 0);
+#pragma unroll
+  for (int k = 0; k < K; ++k) ones &= s[k];
   const uint32_t G = __ballot_sync(kCoopFull, g != 0);
   const uint32_t P = __ballot_sync(kCoopFull, ones == 0xffffffffu && g == 0);
-  uint32_t carry = (uint32_t)((lookahead(G, P) >> lane) & 1u);
+  const uint32_t carry = (uint32_t)((lookahead(G, P) >> lane) & 1u);
+  add_cc(s[0], carry);
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const uint64_t t = (uint64_t)s[k] + carry;
-    s[k] = (uint32_t)t;
-    carry = (uint32_t)(t >> 32);
-  }
+  for (int k = 1; k < K - 1; ++k) addc_cc(s[k], 0);
+  addc(s[K - 1], 0);
 }
 
 // s = x + y + (cin0 at lane 0) over the lanes; x, y must be zero on lanes >= nb.  Returns the carry
@@ -290,9 +296,11 @@ struct Warp {
   LanePlan pf, pl;
   sa N;    // modulus
   sa NI;   // -N^-1 mod R
-  sa T;    // 2*nb*K words of scratch: T (low half of the product being reduced) | Q (quotient)
+  sa T;    // scratch: T (low half of the product being reduced) | Q (quotient), 2*nb*K words per stream
 
   __device__ __forceinline__ sa Q() const { return T + (uint32_t)(nb * K * 4); }
+  // quotient of the second stream of montmul2 (its T | Q area follows the first one)
+  __device__ __forceinline__ sa Q2() const { return T + (uint32_t)(3 * nb * K * 4); }
   __device__ __forceinline__ void load_block(uint32_t (&r)[K], sa num) const {
     if (lane < nb) lds<K>(r, num + (uint32_t)(lane * K * 4));
     else {
@@ -311,33 +319,74 @@ struct Warp {
   }
 };
 
-// out <- (X1*Y1 [+ X2*Y2]) / R mod N, or, with X1 == 0, the Montgomery reduction of the 2nb-block
-// number already lying in w.T (T | Q area).  out may alias any operand.  The quotient q
-// ((T + q N) / R exactly) is left in w.Q().  ONE instance of the three product phases per kernel.
-template <int K>
-__device__ __noinline__ void montmul(const Warp<K> w, sa out, sa X1, sa Y1, sa X2, sa Y2) {
+// One stream of a Montgomery product: out <- (X1*Y1 [+ X2*Y2]) / R mod N, or, with X1 == 0, the
+// Montgomery reduction of the 2nb-block number already lying in the stream's T | Q area.  out may
+// alias any operand of any stream (everything is read before anything is written).  The quotient q
+// ((T + q N) / R exactly) is left in T + nb*K words.
+struct Stream {
+  sa out, X1, Y1, X2, Y2, T;
+};
+
+// NS independent Montgomery products modulo the same N in one instruction stream (NS = 2: the two
+// products of a pair operation).  ONE instance of the three product phases per NS and kernel.
+template <int K, int NS>
+__device__ __forceinline__ void montmul_streams(const Warp<K>& w, const Stream (&st)[NS]) {
   const int lane = w.lane, nb = w.nb;
-  uint32_t e[2 * K + 2], t[K], q[K], u[K];
-  if (X1 != 0) {
-    product<K>(e, w.pf, lane, X1, Y1, X2, Y2);
-    resolve<K>(t, e, nullptr, lane);
-    if (lane < nb) sts<K>(w.T + (uint32_t)(lane * K * 4), t);
-  } else {
-    if (lane < 2 * nb) lds<K>(t, w.T + (uint32_t)(lane * K * 4));
-    else {
+  const uint32_t qoff = (uint32_t)(nb * K * 4), boff = (uint32_t)(lane * K * 4);
+  uint32_t e[NS][2 * K + 2], t[NS][K], r[NS][K];
+  sa x1[NS], y1[NS], x2[NS], y2[NS], zero[NS], tt[NS], qq[NS], nn[NS], ni[NS];
 #pragma unroll
-      for (int k = 0; k < K; ++k) t[k] = 0;
+  for (int s = 0; s < NS; ++s) {
+    x1[s] = st[s].X1 != 0 ? st[s].X1 : st[s].T; y1[s] = st[s].Y1; x2[s] = st[s].X2; y2[s] = st[s].Y2;
+    zero[s] = 0; tt[s] = st[s].T; qq[s] = st[s].T + qoff; nn[s] = w.N; ni[s] = w.NI;
+  }
+  bool any_product = false;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) any_product = any_product || st[s].X1 != 0;
+  if (any_product) {   // (streams given as a ready T skip the first phase; never mixed in practice)
+    product<K, NS>(e, w.pf, lane, x1, y1, x2, y2);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      resolve<K>(t[s], e[s], nullptr, lane);
+      if (lane < nb) sts<K>(tt[s] + boff, t[s]);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (lane < 2 * nb) lds<K>(t[s], tt[s] + boff);
+      else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) t[s][k] = 0;
+      }
     }
   }
   __syncwarp();
-  product<K>(e, w.pl, lane, w.T, w.NI, 0, 0);
-  resolve<K>(q, e, nullptr, lane);
-  if (lane < nb) sts<K>(w.Q() + (uint32_t)(lane * K * 4), q);
+  product<K, NS>(e, w.pl, lane, tt, ni, zero, zero);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    resolve<K>(r[s], e[s], nullptr, lane);
+    if (lane < nb) sts<K>(qq[s] + boff, r[s]);
+  }
   __syncwarp();
-  product<K>(e, w.pf, lane, w.Q(), w.N, 0, 0);
-  resolve<K>(u, e, t, lane);
-  if (lane >= nb && lane < 2 * nb) sts<K>(out + (uint32_t)((lane - nb) * K * 4), u);
+  product<K, NS>(e, w.pf, lane, qq, nn, zero, zero);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    resolve<K>(r[s], e[s], t[s], lane);
+    if (lane >= nb && lane < 2 * nb) sts<K>(st[s].out + (uint32_t)((lane - nb) * K * 4), r[s]);
+  }
   __syncwarp();
+}
+
+template <int K>
+__device__ __noinline__ void montmul(const Warp<K> w, sa out, sa X1, sa Y1, sa X2, sa Y2) {
+  const Stream st[1] = {{out, X1, Y1, X2, Y2, w.T}};
+  montmul_streams<K, 1>(w, st);
+}
+// two products at once; the second stream's scratch is w.T + 2*nb*K words, its quotient after it
+template <int K>
+__device__ __noinline__ void montmul2(const Warp<K> w, sa out0, sa X10, sa Y10, sa X20, sa Y20, sa out1, sa X11, sa Y11) {
+  const Stream st[2] = {{out0, X10, Y10, X20, Y20, w.T}, {out1, X11, Y11, 0, 0, w.T + (uint32_t)(2 * w.nb * K * 4)}};
+  montmul_streams<K, 2>(w, st);
 }
 
 // dst <- b2 - m kept in [0, R) congruent modulo N (pair_fixup of dkg_nsq.cuh): S = b2 + (R - m);
@@ -371,9 +420,9 @@ struct PairAddr {
 // (A, B) <- (A, B) * (C, D)
 template <int K>
 __device__ __noinline__ void pair_mul(const Warp<K> w, const PairAddr pr, sa C, sa D) {
-  montmul<K>(w, pr.B, pr.B, C, pr.A, D);   // B <- REDC(B c + A d)
-  montmul<K>(w, pr.A, pr.A, C, 0, 0);      // A <- REDC(A c), quotient m in Q
-  fixup<K>(w, pr.B, pr.B, w.Q(), pr.dneg);
+  // B <- REDC(B c + A d) and A <- REDC(A c) (quotient m) in one interleaved instruction stream
+  montmul2<K>(w, pr.B, pr.B, C, pr.A, D, pr.A, pr.A, C);
+  fixup<K>(w, pr.B, pr.B, w.Q2(), pr.dneg);
 }
 template <int K>
 __device__ __noinline__ void pair_sqr(const Warp<K> w, const PairAddr pr) {
@@ -382,9 +431,9 @@ __device__ __noinline__ void pair_sqr(const Warp<K> w, const PairAddr pr) {
   shl1<K>(x, w.lane);                      // A < 2N <= R/4: no bit is lost
   w.store_block(pr.A2, x);
   __syncwarp();
-  montmul<K>(w, pr.B, pr.A2, pr.B, 0, 0);  // B <- REDC(2 A B)
-  montmul<K>(w, pr.A, pr.A, pr.A, 0, 0);   // A <- REDC(A^2), quotient m in Q
-  fixup<K>(w, pr.B, pr.B, w.Q(), pr.dneg);
+  // B <- REDC(2 A B) and A <- REDC(A^2) (quotient m) in one interleaved instruction stream
+  montmul2<K>(w, pr.B, pr.A2, pr.B, 0, 0, pr.A, pr.A, pr.A);
+  fixup<K>(w, pr.B, pr.B, w.Q2(), pr.dneg);
 }
 
 // Almost-inverse (Kaliski 1995) of the plain value in `src` modulo N, on lane registers:
@@ -482,18 +531,18 @@ __global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p
   uint32_t* S = reinterpret_cast<uint32_t*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int nb = p.nb, Lc = nb * K;
-  // CTA: the constants; per warp: A B A2 T Q C D XA XB YA YB I0
+  // CTA: the constants; per warp: A B A2 T0 Q0 T1 Q1 C D XA XB YA YB I0
   for (int i = threadIdx.x; i < kCoopNsqConsts * Lc; i += blockDim.x) S[i] = p.consts[i];
   __syncthreads();
   const uint32_t *cONEA = S + 5 * Lc;
   const sa c0 = saddr(S), LB = (uint32_t)(Lc * 4);
   const sa sN = c0, sNI = c0 + LB, sDNEG = c0 + 2 * LB, sR2A = c0 + 3 * LB, sR2B = c0 + 4 * LB, sONEA = c0 + 5 * LB,
            sONEB = c0 + 6 * LB, sTWOA = c0 + 7 * LB, sTWOB = c0 + 8 * LB, sPLAIN1 = c0 + 9 * LB, sZERO = c0 + 10 * LB;
-  uint32_t* W = S + kCoopNsqConsts * Lc + (size_t)warp * 12 * Lc;
-  uint32_t *A = W, *B = W + Lc, *C = W + 5 * Lc, *XA = W + 7 * Lc, *YA = W + 9 * Lc, *I0 = W + 11 * Lc;
+  uint32_t* W = S + kCoopNsqConsts * Lc + (size_t)warp * kCoopNsqWarpBufs * Lc;
+  uint32_t *A = W, *B = W + Lc, *C = W + 7 * Lc, *XA = W + 9 * Lc, *YA = W + 11 * Lc, *I0 = W + 13 * Lc;
   const sa w0 = saddr(W);
-  const sa sA = w0, sB = w0 + LB, sA2 = w0 + 2 * LB, sT = w0 + 3 * LB, sC = w0 + 5 * LB, sD = w0 + 6 * LB,
-           sXA = w0 + 7 * LB, sXB = w0 + 8 * LB, sYA = w0 + 9 * LB, sYB = w0 + 10 * LB, sI0 = w0 + 11 * LB;
+  const sa sA = w0, sB = w0 + LB, sA2 = w0 + 2 * LB, sT = w0 + 3 * LB, sC = w0 + 7 * LB, sD = w0 + 8 * LB,
+           sXA = w0 + 9 * LB, sXB = w0 + 10 * LB, sYA = w0 + 11 * LB, sYB = w0 + 12 * LB, sI0 = w0 + 13 * LB;
 
   Warp<K> w;
   w.lane = lane; w.nb = nb; w.pf.load(p.full, lane); w.pl.load(p.low, lane);

@@ -33,6 +33,7 @@ struct CoopNsqParams {
   CoopPlanTable full, low;
 };
 constexpr int kCoopNsqConsts = 11;
+constexpr int kCoopNsqWarpBufs = 14;   // numbers of nb*K limbs of shared memory per warp
 
 struct CoopGroupedParams {
   const uint32_t* moduli;   // [groups][limbs]

@@ -77,7 +77,7 @@ GroupedFn lookup_grouped_group2(int, int); GroupedFn lookup_grouped_group3(int, 
 GroupedFn lookup_grouped_group4(int, int); GroupedFn lookup_grouped_group5(int, int);
 void launch_group_setup(const GroupedParams& p, cudaStream_t stream);
 // dkg_coop.cu: the cooperative (warp-per-operand) latency kernels
-int coop_max_warps(int K);
+int coop_max_warps(int K, bool pair_kernel);
 cudaError_t launch_coop_nsq(int K, const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
 cudaError_t launch_coop_grouped(int K, const CoopGroupedParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
 }  // namespace dkg
@@ -277,7 +277,7 @@ size_t coop_limit(std::atomic<long>& slot, const char* env_name, long dflt) {
   }
   return (size_t)v;
 }
-constexpr long kCoopMaxDefault = 8192, kCoopGroupedMaxDefault = 16384;
+constexpr long kCoopMaxDefault = 16384, kCoopGroupedMaxDefault = 16384;
 
 }  // namespace
 
@@ -448,8 +448,8 @@ int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out,
 
 // Launch geometry of the cooperative kernels: one instance per warp; spread small batches over the
 // SMs first (one warp per CTA), then stack warps, then go persistent (work ticket).
-void coop_grid(const DeviceState* d, int K, size_t count, int* ctas, int* warps) {
-  const int maxw = dkg::coop_max_warps(K);
+void coop_grid(const DeviceState* d, int K, bool pair_kernel, size_t count, int* ctas, int* warps) {
+  const int maxw = dkg::coop_max_warps(K, pair_kernel);
   if (count <= (size_t)d->sm_count) { *warps = 1; *ctas = (int)count; return; }
   *warps = (int)std::min<size_t>(maxw, (count + d->sm_count - 1) / d->sm_count);
   *ctas = (int)std::min<size_t>((count + *warps - 1) / *warps, (size_t)d->sm_count * std::max(1, maxw / *warps));
@@ -462,7 +462,7 @@ int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d
   DeviceState* d = ctx->dev;
   const int Lc = ctx->cLc;
   int ctas = 1, warps = 1;
-  coop_grid(d, ctx->cK, count, &ctas, &warps);
+  coop_grid(d, ctx->cK, true, count, &ctas, &warps);
   const size_t per_warp = ((size_t)ctx->tab_entries + 1) * 2 * Lc;
   const size_t pair_words = count * (size_t)(2 * Lc);
   int rc = ensure_scratch(d, (size_t)ctas * warps * per_warp);
@@ -478,7 +478,7 @@ int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d
   q.pairs_in = pairs; q.pairs_out = pairs; q.status = d_status; q.count = count; q.nb = ctx->cnb; q.negative = ctx->negative;
   q.consts = ctx->d_cconsts; q.ops = ctx->d_ops; q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd;
   q.scratch = d->scratch; q.scratch_per_warp = per_warp; q.counter = d->counter; q.full = ctx->cfull; q.low = ctx->clow;
-  const size_t smem = ((size_t)dkg::kCoopNsqConsts + (size_t)12 * warps) * Lc * 4;
+  const size_t smem = ((size_t)dkg::kCoopNsqConsts + (size_t)dkg::kCoopNsqWarpBufs * warps) * Lc * 4;
   CUDA_TRY(dkg::launch_coop_nsq(ctx->cK, q, ctas, warps, smem, stream));
   dkg::NsqIoParams x = e;
   x.in = pairs; x.out = d_out; x.mrows = d_mrows; x.m_limbs = m_limbs;
@@ -1182,7 +1182,7 @@ bool plan_coop_grouped(DeviceState* d, const uint32_t* moduli, size_t groups, in
   plan->Lc = plan->K * plan->nb;
   plan->wbits = choose_window(ebits);
   plan->ndigits = std::max(1, (ebits + plan->wbits - 1) / plan->wbits);
-  coop_grid(d, plan->K, count, &plan->ctas, &plan->warps);
+  coop_grid(d, plan->K, false, count, &plan->ctas, &plan->warps);
   plan->smem = (size_t)9 * plan->warps * plan->Lc * 4;
   plan->per_warp = (((size_t)1 << plan->wbits) - 1) * plan->Lc;
   plan->full = make_coop_plan(plan->nb, 2 * plan->nb - 1);

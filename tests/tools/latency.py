@@ -45,17 +45,23 @@ def main() -> None:
 
     cores = os.cpu_count() or 1
     rng = random.Random(99)
+    import math
+
     half = args.key_bits // 2 + 1          # reference-shaped: N is key_length + 2..4 bits
     p = rng.getrandbits(half) | 1 | (1 << (half - 1))
     q = rng.getrandbits(half) | 1 | (1 << (half - 1))
-    n = p * q
+    n = p * q                              # not a biprime (cost is identical): bases are drawn as units
     n2 = n * n
     ebits = 2 * args.key_bits + 100
     sizes = [1, 32, 1024] if args.quick else [1, 8, 32, 128, 512, 1024, 4096, 16384]
     for sign in (1, -1):
         e = sign * (rng.getrandbits(ebits) | (1 << (ebits - 1)))
         for B in sizes:
-            vals = [rng.randrange(1, n2) for _ in range(min(B, 64))]
+            vals = []
+            while len(vals) < min(B, 64):
+                v = rng.randrange(1, n2)
+                if math.gcd(v, n) == 1:
+                    vals.append(v)
             rows = ints_to_limbs((vals * (B // len(vals) + 1))[:B], (n2.bit_length() + 31) // 32)
             line = {"op": "partial_decrypt", "key_bits": args.key_bits, "exp_sign": sign, "batch": B}
             for label, limit in (("coop_ms", 1 << 30), ("wave_ms", 0)):
