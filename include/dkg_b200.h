@@ -28,7 +28,9 @@
  *    unit and the exponent is negative: the reference raises ZeroDivisionError from mod_inv),
  *    DKG_STATUS_NOT_DIVISIBLE (combine: (x-1) % N != 0: the reference raises ValueError,
  *    paillier_shared_key.py:119-123).  Rows with a non-zero status are zero-filled.
- *  - Every input value must be < the modulus of its context (the reference's ciphertexts are).
+ *  - Every input value must be < the modulus of its context (the reference's ciphertexts are); a
+ *    modexp row that is not gets DKG_STATUS_OUT_OF_RANGE and a zero result instead of a silently
+ *    wrong one (the Python-int wrappers reduce first, as the reference's pow_mod does).
  *  - A context is bound to one device and one internal stream; calls on one context serialise.
  *    The *_device variants take device pointers and a cudaStream_t (as void*) and are
  *    asynchronous with respect to the host; everything else is synchronous.
@@ -55,6 +57,7 @@ extern "C" {
 #define DKG_STATUS_OK 0
 #define DKG_STATUS_NOT_INVERTIBLE 1
 #define DKG_STATUS_NOT_DIVISIBLE 2
+#define DKG_STATUS_OUT_OF_RANGE 3   /* modexp: the row is not below the modulus (the result row is zero) */
 
 #define DKG_MAX_LIMBS 272 /* widest modulus the compiled kernel shapes cover (8704 bits) */
 
@@ -126,6 +129,37 @@ int dkg_combine_batch(dkg_combine_ctx* ctx, const uint32_t* partials, uint32_t* 
                       uint8_t* status, size_t count);
 int dkg_combine_batch_device(dkg_combine_ctx* ctx, const uint32_t* d_partials, uint32_t* d_out,
                              uint8_t* d_status, size_t count, void* stream);
+
+/* ---- in-process threshold decryption, sharded by index over the GPUs of one box ------------------ */
+/* All d+1 parties' keys in one process (DistributedPaillier with distributed=False: the reference's
+ * test / benchmark set-up, distributed_keygen.py:203-226): the two loops of _decrypt_sequence_raw
+ * (:463-466 partial decryptions, :510-515 combinations) for every party in one call.  devices: the
+ * GPUs to shard over (one host thread + two streams each; rows [count*r/ndev, count*(r+1)/ndev) go to
+ * device r; results land in disjoint slices of the caller's arrays; no inter-GPU collective).
+ * exponents: [shares][exp_limbs] magnitudes, negative[shares] their signs (party p+1 at index p,
+ * paillier_shared_key.py:70-85).  Buffers may be pageable; page-locked ones (dkg_host_register) copy
+ * at full PCIe rate. */
+typedef struct dkg_threshold_ctx dkg_threshold_ctx;
+int dkg_threshold_ctx_create(const int* devices, int ndev, const uint32_t* n, int n_limbs,
+                             const uint32_t* theta_inv, int shares, const uint32_t* exponents,
+                             int exp_limbs, const uint8_t* negative, dkg_threshold_ctx** out);
+void dkg_threshold_ctx_destroy(dkg_threshold_ctx* ctx);
+/* info[0]=devices, [1]=shares, [2]=limbs of N, [3]=limbs of N^2 */
+int dkg_threshold_info(const dkg_threshold_ctx* ctx, int info[4]);
+/* ciphertexts [count][n2_limbs] -> plaintexts [count][n_limbs]; the ciphertexts are uploaded once,
+ * the partial decryptions stay on the device unless `partials` ([shares][count][n2_limbs]) is given.
+ * status[count] (or NULL): the first party's non-zero modexp status, else the combination's. */
+int dkg_threshold_decrypt_batch(dkg_threshold_ctx* ctx, const uint32_t* ciphertexts,
+                                uint32_t* plaintexts, uint32_t* partials, uint8_t* status, size_t count);
+/* one party's partial decryptions (what a distributed party computes for its broadcast) */
+int dkg_threshold_partial_decrypt_batch(dkg_threshold_ctx* ctx, int party, const uint32_t* ciphertexts,
+                                        uint32_t* out, uint8_t* status, size_t count);
+/* combination of received partials [shares][count][n2_limbs] */
+int dkg_threshold_combine_batch(dkg_threshold_ctx* ctx, const uint32_t* partials, uint32_t* plaintexts,
+                                uint8_t* status, size_t count);
+/* cudaHostRegister / cudaHostUnregister of a caller buffer (portable across the devices) */
+int dkg_host_register(void* ptr, size_t bytes);
+int dkg_host_unregister(void* ptr);
 
 /* ---- encryption: (1 + m N) * r^N mod N^2 ---------------------------------------------------- */
 /* ctx: a modexp context created with modulus = N^2 and exponent = N.  r: [count][n_limbs],

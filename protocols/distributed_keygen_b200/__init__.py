@@ -10,11 +10,11 @@ no CPU fallback.
 """
 from . import _native  # noqa: F401  (fails loudly if the CUDA engine is not built)
 from .engine import (  # noqa: F401
-    CombineContext, EncryptContext, ModexpContext, biprime_v_batch_limbs, biprime_verdict, jacobi_batch, launch_count,
+    CombineContext, EncryptContext, ModexpContext, ThresholdContext, pinned, biprime_v_batch_limbs, biprime_verdict, jacobi_batch, launch_count,
     modexp_grouped, modexp_grouped_limbs, small_prime_sieve,
 )
 from . import distributed_keygen  # noqa: F401
 from .paillier_shared_key import IntegerShares, PaillierSharedKey  # noqa: F401
 
-__all__ = ["CombineContext", "EncryptContext", "ModexpContext", "PaillierSharedKey", "IntegerShares", "launch_count", "modexp_grouped",
+__all__ = ["ThresholdContext", "pinned", "CombineContext", "EncryptContext", "ModexpContext", "PaillierSharedKey", "IntegerShares", "launch_count", "modexp_grouped",
            "modexp_grouped_limbs", "distributed_keygen"]

@@ -23,6 +23,7 @@ DKG_ERR_NOT_IMPLEMENTED = 5
 STATUS_OK = 0
 STATUS_NOT_INVERTIBLE = 1
 STATUS_NOT_DIVISIBLE = 2
+STATUS_OUT_OF_RANGE = 3
 
 # every symbol include/dkg_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
@@ -32,6 +33,8 @@ EXPORTS = [
     "dkg_modexp_batch", "dkg_modexp_batch_device",
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
     "dkg_combine_batch", "dkg_combine_batch_device",
+    "dkg_threshold_ctx_create", "dkg_threshold_ctx_destroy", "dkg_threshold_info", "dkg_threshold_decrypt_batch",
+    "dkg_threshold_partial_decrypt_batch", "dkg_threshold_combine_batch", "dkg_host_register", "dkg_host_unregister",
     "dkg_encrypt_batch", "dkg_modexp_grouped",
     "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve", "dkg_biprime_verdict",
     "dkg_wire_encode_rows", "dkg_wire_decode_rows",
@@ -72,6 +75,16 @@ def _load() -> ctypes.CDLL:
     lib.dkg_combine_n2_limbs.argtypes = [c_void]
     lib.dkg_combine_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_combine_batch_device.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t, c_void]
+    lib.dkg_threshold_ctx_create.argtypes = [c_void, ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int,
+                                             c_u8p, ctypes.POINTER(c_void)]
+    lib.dkg_threshold_ctx_destroy.argtypes = [c_void]
+    lib.dkg_threshold_ctx_destroy.restype = None
+    lib.dkg_threshold_info.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 4)]
+    lib.dkg_threshold_decrypt_batch.argtypes = [c_void, c_u32p, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
+    lib.dkg_threshold_partial_decrypt_batch.argtypes = [c_void, ctypes.c_int, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
+    lib.dkg_threshold_combine_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
+    lib.dkg_host_register.argtypes = [c_void, ctypes.c_size_t]
+    lib.dkg_host_unregister.argtypes = [c_void]
     lib.dkg_encrypt_batch.argtypes = [c_void, c_u32p, ctypes.c_int, c_u32p, c_u32p, c_u32p, ctypes.c_size_t]
     lib.dkg_modexp_grouped.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u32p, c_u32p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
     lib.dkg_biprime_v_batch.argtypes = [ctypes.c_int, c_u32p, c_u32p, ctypes.c_int, c_u32p, ctypes.c_int, ctypes.c_int,

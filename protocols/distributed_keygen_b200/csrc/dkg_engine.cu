@@ -399,8 +399,29 @@ int inversion_chain_warps(const DeviceState* d, const dkg_modexp_ctx* ctx, unsig
   return (int)std::max<unsigned long long>(nchain, 1);
 }
 
+int launch_modexp_inner(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
+                        const uint32_t* d_final_mul, size_t count, cudaStream_t stream);
+
+// out-of-range rows (>= modulus) are flagged and zeroed after the compute kernels
+int launch_range_check(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status, size_t count,
+                       cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((count * 32 + 255) / 256);
+  dkg::range_check_kernel<<<blocks, 256, 0, stream>>>(d_bases, ctx->d_consts, ctx->limbs, count, d_out, d_status);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return DKG_OK;
+}
+
 int launch_modexp(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
                   const uint32_t* d_final_mul, size_t count, cudaStream_t stream) {
+  if (count == 0) return DKG_OK;
+  int rc = launch_modexp_inner(ctx, d_bases, d_out, d_status, d_final_mul, count, stream);
+  if (rc != DKG_OK) return rc;
+  return launch_range_check(ctx, d_bases, d_out, d_status, count, stream);
+}
+
+int launch_modexp_inner(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
+                        const uint32_t* d_final_mul, size_t count, cudaStream_t stream) {
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
@@ -1432,3 +1453,241 @@ extern "C" int dkg_biprime_verdict(int device, const uint32_t* moduli, const uin
   for (size_t g = 0; g < groups; ++g) ok[g] = (uint8_t)(res[g] ? 1 : 0);
   return DKG_OK;
 }
+
+// ---- one call, several GPUs: in-process threshold decryption --------------------------------------
+// ciphertexts are independent, so a batch shards by index across the GPUs of
+// one box -- one host thread + two streams per device, H2D of each shard from the caller's array,
+// results D2H into disjoint slices of the caller's arrays (the "host gather").  No inter-GPU
+// collective.  With all parties' keys in one process (DistributedPaillier with distributed=False,
+// the reference's test and benchmark set-up, distributed_keygen.py:203-226) the d+1 partial
+// decryptions and the combination of _decrypt_sequence_raw (:463-466, :510-515) run back to back on
+// the device: the ciphertexts are uploaded once, the partials never visit the host unless asked for.
+#include <thread>
+
+struct dkg_threshold_ctx {
+  struct Dev {
+    DeviceState* dev = nullptr;
+    std::vector<dkg_modexp_ctx*> parties;
+    dkg_combine_ctx* combine = nullptr;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+  };
+  int shares = 0, n_limbs = 0, l2 = 0;
+  size_t chunk_rows = 1 << 18;
+  std::vector<Dev> devs;
+};
+
+namespace {
+
+struct Shard { size_t lo, hi; };
+std::vector<Shard> shard_rows(size_t count, size_t parts) {
+  std::vector<Shard> out(parts);
+  for (size_t r = 0; r < parts; ++r) out[r] = Shard{count * r / parts, count * (r + 1) / parts};
+  return out;
+}
+
+// what one device does with its shard, chunk by chunk, alternating between its two streams so the
+// copies of one chunk overlap the kernels of the other.  mode 0: decrypt (partials optional),
+// 1: one party's partial decryption, 2: combination of given partials.
+struct ThresholdJob {
+  int mode = 0, party = 0;
+  const uint32_t* in = nullptr;        // mode 0/1: ciphertexts [count][l2]; mode 2: partials [shares][count][l2]
+  uint32_t* plain = nullptr;           // [count][n_limbs]  (mode 0/2)
+  uint32_t* partials = nullptr;        // mode 0: optional [shares][count][l2]; mode 1: [count][l2]
+  uint8_t* status = nullptr;           // [count] or null
+  size_t count = 0;                    // rows of the whole call (stride between shares)
+};
+
+int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const ThresholdJob& job, Shard sh, std::string* err) {
+  auto failed = [&](int code, const std::string& msg) { *err = msg; return code; };
+#define TRY_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) return failed(DKG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+  if (sh.hi <= sh.lo) return DKG_OK;
+  TRY_CUDA(cudaSetDevice(dv.dev->device));
+  const int S = t->shares, l2 = t->l2, ln = t->n_limbs;
+  const size_t rows_max = std::min(t->chunk_rows, sh.hi - sh.lo);
+  const size_t row_b = (size_t)l2 * 4, plain_b = (size_t)ln * 4;
+  struct Buf { uint32_t *in = nullptr, *part = nullptr, *out = nullptr; uint8_t* st = nullptr; std::vector<uint8_t> host_st; size_t lo = 0, rows = 0; bool busy = false; } buf[2];
+  const bool need_part = job.mode != 1;       // [S][rows][l2] on the device
+  for (int b = 0; b < 2; ++b) {
+    cudaStream_t s = dv.streams[b];
+    if (job.mode != 2) TRY_CUDA(cudaMallocAsync(&buf[b].in, rows_max * row_b, s));
+    TRY_CUDA(cudaMallocAsync(&buf[b].part, rows_max * row_b * (need_part ? S : 1), s));
+    if (job.mode != 1) TRY_CUDA(cudaMallocAsync(&buf[b].out, rows_max * plain_b, s));
+    TRY_CUDA(cudaMallocAsync(&buf[b].st, rows_max * (size_t)(S + 1), s));
+    buf[b].host_st.resize(rows_max * (size_t)(S + 1));
+  }
+  auto finish = [&](Buf& B, cudaStream_t s) -> int {
+    if (!B.busy) return DKG_OK;
+    TRY_CUDA(cudaStreamSynchronize(s));
+    B.busy = false;
+    if (job.status) {
+      for (size_t i = 0; i < B.rows; ++i) {
+        uint8_t st = 0;
+        if (job.mode == 1) st = B.host_st[i];
+        else {
+          if (job.mode == 0)
+            for (int p = 0; p < S && st == 0; ++p) st = B.host_st[(size_t)p * B.rows + i];
+          if (st == 0) st = B.host_st[(size_t)S * B.rows + i];
+        }
+        job.status[B.lo + i] = st;
+      }
+    }
+    return DKG_OK;
+  };
+  int which = 0, rc = DKG_OK;
+  for (size_t lo = sh.lo; lo < sh.hi && rc == DKG_OK; lo += rows_max, which ^= 1) {
+    Buf& B = buf[which];
+    cudaStream_t s = dv.streams[which];
+    rc = finish(B, s);
+    if (rc != DKG_OK) break;
+    const size_t rows = std::min(rows_max, sh.hi - lo);
+    B.lo = lo; B.rows = rows; B.busy = true;
+    if (job.mode == 2) {
+      for (int p = 0; p < S; ++p)
+        TRY_CUDA(cudaMemcpyAsync(B.part + (size_t)p * rows * l2, job.in + ((size_t)p * job.count + lo) * l2, rows * row_b, cudaMemcpyHostToDevice, s));
+    } else {
+      TRY_CUDA(cudaMemcpyAsync(B.in, job.in + lo * l2, rows * row_b, cudaMemcpyHostToDevice, s));
+    }
+    {
+      DeviceLease lease(dv.dev, s);
+      if (job.mode == 1) {
+        rc = launch_modexp(dv.parties[job.party], B.in, B.part, B.st, nullptr, rows, s);
+      } else {
+        if (job.mode == 0)
+          for (int p = 0; p < S && rc == DKG_OK; ++p)
+            rc = launch_modexp(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, nullptr, rows, s);
+        if (rc == DKG_OK) rc = launch_combine(dv.combine, B.part, B.out, B.st + (size_t)S * rows, rows, s);
+      }
+      if (rc != DKG_OK) { *err = g_err; break; }
+    }
+    if (job.mode == 1) {
+      TRY_CUDA(cudaMemcpyAsync(job.partials + lo * l2, B.part, rows * row_b, cudaMemcpyDeviceToHost, s));
+      if (job.status) TRY_CUDA(cudaMemcpyAsync(B.host_st.data(), B.st, rows, cudaMemcpyDeviceToHost, s));
+    } else {
+      TRY_CUDA(cudaMemcpyAsync(job.plain + lo * ln, B.out, rows * plain_b, cudaMemcpyDeviceToHost, s));
+      if (job.mode == 0 && job.partials)
+        for (int p = 0; p < S; ++p)
+          TRY_CUDA(cudaMemcpyAsync(job.partials + ((size_t)p * job.count + lo) * l2, B.part + (size_t)p * rows * l2, rows * row_b, cudaMemcpyDeviceToHost, s));
+      if (job.status) TRY_CUDA(cudaMemcpyAsync(B.host_st.data(), B.st, rows * (size_t)(S + 1), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  for (int b = 0; b < 2; ++b) {
+    const int r2 = finish(buf[b], dv.streams[b]);
+    if (rc == DKG_OK) rc = r2;
+    cudaStream_t s = dv.streams[b];
+    if (buf[b].in) cudaFreeAsync(buf[b].in, s);
+    if (buf[b].part) cudaFreeAsync(buf[b].part, s);
+    if (buf[b].out) cudaFreeAsync(buf[b].out, s);
+    if (buf[b].st) cudaFreeAsync(buf[b].st, s);
+  }
+  return rc;
+#undef TRY_CUDA
+}
+
+int run_threshold(dkg_threshold_ctx* t, const ThresholdJob& job) {
+  if (job.count == 0) return DKG_OK;
+  const size_t ndev = t->devs.size();
+  const std::vector<Shard> shards = shard_rows(job.count, ndev);
+  std::vector<int> rcs(ndev, DKG_OK);
+  std::vector<std::string> errs(ndev);
+  std::vector<std::thread> threads;
+  for (size_t r = 1; r < ndev; ++r)
+    threads.emplace_back([&, r] { rcs[r] = run_threshold_shard(t, t->devs[r], job, shards[r], &errs[r]); });
+  rcs[0] = run_threshold_shard(t, t->devs[0], job, shards[0], &errs[0]);
+  for (auto& th : threads) th.join();
+  for (size_t r = 0; r < ndev; ++r)
+    if (rcs[r] != DKG_OK) return fail(rcs[r], "device " + std::to_string(t->devs[r].dev->device) + ": " + errs[r]);
+  return DKG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dkg_threshold_ctx_create(const int* devices, int ndev, const uint32_t* n, int n_limbs, const uint32_t* theta_inv,
+                             int shares, const uint32_t* exponents, int exp_limbs, const uint8_t* negative,
+                             dkg_threshold_ctx** out) {
+  if (!devices || ndev <= 0 || !n || !theta_inv || !exponents || !negative || !out || shares < 1 || exp_limbs <= 0 || n_limbs <= 0)
+    return fail(DKG_ERR_INVALID, "null/empty argument");
+  auto* t = new dkg_threshold_ctx();
+  t->shares = shares;
+  if (long c = env_long("DKG_CHUNK_ROWS", 0); c > 0) t->chunk_rows = (size_t)c;
+  for (int i = 0; i < ndev; ++i) {
+    dkg_threshold_ctx::Dev dv;
+    int rc = device_state(devices[i], &dv.dev);
+    for (int p = 0; p < shares && rc == DKG_OK; ++p) {
+      dkg_modexp_ctx* c = nullptr;
+      rc = dkg_modexp_ctx_create_nsq(devices[i], n, n_limbs, exponents + (size_t)p * exp_limbs, exp_limbs, negative[p], &c);
+      if (rc == DKG_OK) dv.parties.push_back(c);
+    }
+    if (rc == DKG_OK) rc = dkg_combine_ctx_create(devices[i], n, n_limbs, theta_inv, shares, &dv.combine);
+    if (rc == DKG_OK) {
+      cudaSetDevice(devices[i]);
+      for (int b = 0; b < 2 && rc == DKG_OK; ++b)
+        if (cudaStreamCreateWithFlags(&dv.streams[b], cudaStreamNonBlocking) != cudaSuccess) rc = fail(DKG_ERR_CUDA, "stream creation failed");
+    }
+    t->devs.push_back(dv);
+    if (rc != DKG_OK) { const std::string keep = g_err; dkg_threshold_ctx_destroy(t); g_err = keep; return rc; }
+  }
+  t->n_limbs = t->devs[0].combine->ln;
+  t->l2 = t->devs[0].combine->l2;
+  *out = t;
+  return DKG_OK;
+}
+
+void dkg_threshold_ctx_destroy(dkg_threshold_ctx* t) {
+  if (!t) return;
+  for (auto& dv : t->devs) {
+    if (dv.dev) cudaSetDevice(dv.dev->device);
+    for (auto* c : dv.parties) dkg_modexp_ctx_destroy(c);
+    dkg_combine_ctx_destroy(dv.combine);
+    for (auto s : dv.streams) if (s) cudaStreamDestroy(s);
+  }
+  delete t;
+}
+
+int dkg_threshold_info(const dkg_threshold_ctx* t, int info[4]) {
+  if (!t || !info) return fail(DKG_ERR_INVALID, "null argument");
+  info[0] = (int)t->devs.size(); info[1] = t->shares; info[2] = t->n_limbs; info[3] = t->l2;
+  return DKG_OK;
+}
+
+int dkg_threshold_decrypt_batch(dkg_threshold_ctx* t, const uint32_t* ciphertexts, uint32_t* plaintexts, uint32_t* partials,
+                                uint8_t* status, size_t count) {
+  if (!t || (count && (!ciphertexts || !plaintexts))) return fail(DKG_ERR_INVALID, "null argument");
+  ThresholdJob job;
+  job.mode = 0; job.in = ciphertexts; job.plain = plaintexts; job.partials = partials; job.status = status; job.count = count;
+  return run_threshold(t, job);
+}
+
+int dkg_threshold_partial_decrypt_batch(dkg_threshold_ctx* t, int party, const uint32_t* ciphertexts, uint32_t* out,
+                                        uint8_t* status, size_t count) {
+  if (!t || party < 0 || party >= t->shares || (count && (!ciphertexts || !out))) return fail(DKG_ERR_INVALID, "bad argument");
+  ThresholdJob job;
+  job.mode = 1; job.party = party; job.in = ciphertexts; job.partials = out; job.status = status; job.count = count;
+  return run_threshold(t, job);
+}
+
+int dkg_threshold_combine_batch(dkg_threshold_ctx* t, const uint32_t* partials, uint32_t* plaintexts, uint8_t* status, size_t count) {
+  if (!t || (count && (!partials || !plaintexts))) return fail(DKG_ERR_INVALID, "null argument");
+  ThresholdJob job;
+  job.mode = 2; job.in = partials; job.plain = plaintexts; job.status = status; job.count = count;
+  return run_threshold(t, job);
+}
+
+/* page-lock / release a caller buffer so that the copies above run at full PCIe rate */
+int dkg_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(DKG_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return DKG_OK;
+}
+int dkg_host_unregister(void* ptr) {
+  if (!ptr) return fail(DKG_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaHostUnregister(ptr));
+  return DKG_OK;
+}
+
+}  // extern "C"

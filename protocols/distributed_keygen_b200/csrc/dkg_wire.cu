@@ -46,7 +46,7 @@ inline size_t put_be(uint8_t* p, uint8_t tag, uint64_t v, int bytes) {
 // one integer; p may be null (size query)
 inline size_t encode_row(uint8_t* p, const uint32_t* row, int limbs) {
   const int bits = dkg_host::bit_length(row, limbs);
-  if (bits < 64) {
+  if (bits <= 64) {   // native msgpack integers cover the whole uint64 range (0xcf)
     const uint64_t v = (uint64_t)row[0] | (limbs > 1 ? (uint64_t)row[1] << 32 : 0);
     if (v < 128) {
       if (p) p[0] = (uint8_t)v;
@@ -100,6 +100,9 @@ extern "C" int dkg_wire_decode_rows(const uint8_t* buf, size_t len, int limbs, u
   else if (b0 == 0xdc && len >= 3) { count = ((size_t)buf[1] << 8) | buf[2]; pos = 3; }
   else if (b0 == 0xdd && len >= 5) { for (int k = 0; k < 4; ++k) count = (count << 8) | buf[1 + k]; pos = 5; }
   else { dkg_set_error("dkg_wire_decode_rows: not a msgpack array"); return DKG_ERR_INVALID; }
+  // every element takes at least one byte: a header that promises more than the buffer holds is
+  // malformed (and must not size an allocation on the caller's side)
+  if (count > len - pos) { dkg_set_error("dkg_wire_decode_rows: array header longer than the message"); return DKG_ERR_INVALID; }
   *count_out = count;
   if (!rows) { if (consumed) *consumed = 0; return DKG_OK; }  // count query
   if (capacity_rows < count) { dkg_set_error("dkg_wire_decode_rows: row buffer too small"); return DKG_ERR_NOMEM; }

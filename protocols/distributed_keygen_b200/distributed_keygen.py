@@ -143,6 +143,40 @@ def small_prime_divisors_test_batch(prime_list: Sequence[int], moduli: Sequence[
     return small_prime_sieve(moduli, prime_list, device)
 
 
+def threshold_context(keys: Mapping[int, PaillierSharedKey], devices: Sequence[int] | None = None):
+    """One multi-GPU context for all in-process parties of a key (``engine.ThresholdContext``): the
+    exponents of parties 1..degree+1, theta^-1 and N."""
+    from .engine import ThresholdContext
+
+    any_key = next(iter(keys.values()))
+    need = range(1, any_key.share.degree + 2)
+    return ThresholdContext(any_key.n, any_key.theta_inv, {i: keys[i].partial_decrypt_exponent() for i in need}, devices)
+
+
+def decrypt_sequence_limbs(
+    keys: Mapping[int, PaillierSharedKey], ciphertext_rows: np.ndarray, devices: Sequence[int] | None = None
+) -> np.ndarray:
+    """``decrypt_sequence_local`` on limb rows, sharded over ``devices`` (default: every GPU of the
+    box): [count][limbs(N^2)] -> [count][limbs(N)].  Same exceptions as the reference's per-element
+    calls: ``ZeroDivisionError`` (a ciphertext that is not a unit under a negative exponent),
+    ``ValueError`` (combined value minus one not divisible by N)."""
+    ctx = threshold_context(keys, devices)
+    try:
+        plain, status, _ = ctx.decrypt_limbs(ciphertext_rows)
+    finally:
+        ctx.close()
+    if (status == 1).any():
+        raise ZeroDivisionError("ciphertext not invertible modulo N^2")
+    if (status == 3).any():
+        raise ValueError("ciphertext value is not below N^2")
+    if status.any():
+        raise ValueError(
+            "Combined decryption minus one is not divisible by N. This might be caused by the "
+            "fact that the ciphertext that is being decrypted, differs between the parties."
+        )
+    return plain
+
+
 def decrypt_sequence_local(
     keys: Mapping[int, PaillierSharedKey], ciphertexts: Sequence[object], combiner: int | None = None
 ) -> list[int]:
@@ -164,6 +198,8 @@ def partial_decryption_message(key: PaillierSharedKey, ciphertext_rows: np.ndarr
     from . import wire
 
     rows, status = key.partial_decrypt_limbs(ciphertext_rows)
+    if (status == 3).any():
+        raise ValueError("ciphertext value is not below N^2")
     if status.any():
         raise ZeroDivisionError("ciphertext not invertible modulo N^2")
     return wire.pack_partial_decryption_message(rows)

@@ -343,3 +343,106 @@ def biprime_verdict(
                                         ok.ctypes.data, groups, limbs)
     )
     return [bool(o) and e for o, e in zip(ok, enough)]
+
+
+class ThresholdContext:
+    """In-process threshold decryption sharded over the GPUs of one box (C ABI
+    ``dkg_threshold_*``): all d+1 parties' exponents for one key, i.e. both loops of
+    ``DistributedPaillier._decrypt_sequence_raw`` (``distributed_keygen.py:463-466, 510-515``) for
+    every party, with the ciphertexts uploaded once and the partials kept on the device.
+    ``exponents`` maps party index (1..d+1) to its signed exponent
+    (``PaillierSharedKey.partial_decrypt_exponent``)."""
+
+    def __init__(self, n: int, theta_inv: int, exponents: dict[int, int], devices: Sequence[int] | None = None) -> None:
+        parties = sorted(exponents)
+        if parties != list(range(1, len(parties) + 1)):
+            raise KeyError("exponents of parties 1..d+1 are needed")
+        self.n = n
+        self.shares = len(parties)
+        self.devices = list(devices) if devices is not None else list(range(max(1, _native.device_count())))
+        self.n_limbs = limbs_for_bits(n.bit_length())
+        self.n2_limbs = limbs_for_bits((n * n).bit_length())
+        exp_limbs = limbs_for_bits(max(max(abs(e).bit_length() for e in exponents.values()), 1))
+        exps = ints_to_limbs([abs(exponents[p]) for p in parties], exp_limbs)
+        neg = np.array([1 if exponents[p] < 0 else 0 for p in parties], dtype=np.uint8)
+        dev = np.array(self.devices, dtype=np.int32)
+        self._n = int_to_limbs(n, self.n_limbs)
+        self._th = int_to_limbs(theta_inv % n, self.n_limbs)
+        handle = ctypes.c_void_p()
+        _native.check(_native.lib.dkg_threshold_ctx_create(
+            dev.ctypes.data, len(self.devices), self._n.ctypes.data, self.n_limbs, self._th.ctypes.data, self.shares,
+            exps.ctypes.data, exp_limbs, neg.ctypes.data, ctypes.byref(handle)))
+        self._h = handle
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _native.lib.dkg_threshold_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _rows(self, arr: np.ndarray, width: int) -> np.ndarray:
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        if arr.shape[-1] != width:
+            raise ValueError(f"rows must have {width} limbs")
+        return arr
+
+    def decrypt_limbs(self, ciphertexts: np.ndarray, want_partials: bool = False,
+                      out: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray | None]:
+        """[count, n2_limbs] -> (plaintexts [count, n_limbs], status [count], partials [shares, count, n2_limbs] | None)."""
+        cts = self._rows(ciphertexts, self.n2_limbs)
+        count = cts.shape[0]
+        plain = out if out is not None else np.zeros((count, self.n_limbs), dtype=np.uint32)
+        status = np.zeros(count, dtype=np.uint8)
+        parts = np.zeros((self.shares, count, self.n2_limbs), dtype=np.uint32) if want_partials else None
+        _native.check(_native.lib.dkg_threshold_decrypt_batch(
+            self._h, cts.ctypes.data, plain.ctypes.data, parts.ctypes.data if parts is not None else None,
+            status.ctypes.data, count))
+        return plain, status, parts
+
+    def partial_decrypt_limbs(self, party: int, ciphertexts: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        cts = self._rows(ciphertexts, self.n2_limbs)
+        count = cts.shape[0]
+        out = np.zeros_like(cts)
+        status = np.zeros(count, dtype=np.uint8)
+        _native.check(_native.lib.dkg_threshold_partial_decrypt_batch(
+            self._h, party - 1, cts.ctypes.data, out.ctypes.data, status.ctypes.data, count))
+        return out, status
+
+    def combine_limbs(self, partials: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        parts = self._rows(partials, self.n2_limbs)
+        if parts.ndim != 3 or parts.shape[0] != self.shares:
+            raise ValueError(f"partials must have shape [{self.shares}, count, {self.n2_limbs}]")
+        count = parts.shape[1]
+        plain = np.zeros((count, self.n_limbs), dtype=np.uint32)
+        status = np.zeros(count, dtype=np.uint8)
+        _native.check(_native.lib.dkg_threshold_combine_batch(
+            self._h, parts.ctypes.data, plain.ctypes.data, status.ctypes.data, count))
+        return plain, status
+
+
+class pinned:
+    """Context manager: page-lock a numpy array for the duration of the block (full-rate PCIe copies)."""
+
+    def __init__(self, *arrays: np.ndarray) -> None:
+        self.arrays = [a for a in arrays if a is not None and a.nbytes]
+
+    def __enter__(self):
+        done = []
+        try:
+            for a in self.arrays:
+                _native.check(_native.lib.dkg_host_register(a.ctypes.data, a.nbytes))
+                done.append(a)
+        except Exception:
+            for a in done:
+                _native.lib.dkg_host_unregister(a.ctypes.data)
+            raise
+        return self
+
+    def __exit__(self, *exc) -> None:
+        for a in self.arrays:
+            _native.lib.dkg_host_unregister(a.ctypes.data)

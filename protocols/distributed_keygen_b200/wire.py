@@ -59,7 +59,7 @@ def decode_int_rows(buf: bytes, limbs: int, offset: int = 0) -> tuple[np.ndarray
         rows = np.empty((count.value, limbs), dtype=np.uint32)
         check(lib.dkg_wire_decode_rows(_ptr(arr), arr.size, limbs, _ptr(rows), count.value,
                                        ctypes.byref(count), ctypes.byref(used)))
-    except DkgError as exc:
+    except (DkgError, MemoryError, OverflowError) as exc:
         raise ValueError(str(exc)) from None
     return rows, offset + used.value
 

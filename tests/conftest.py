@@ -38,6 +38,7 @@ def biprime_vectors():
     return load_golden("biprime_vectors.json")
 
 
-# scratch experiments and measurement tools live under tests/ (they use the oracle as a checker)
-# but are not test modules
-collect_ignore_glob = ["scratch/*", "tools/*"]
+# measurement / profiling tools live under tests/tools (they may use the oracle as a checker) but are
+# not test modules; coop_model.py and ref_harness.py are helpers imported by tests
+collect_ignore_glob = ["tools/*"]
+collect_ignore = ["coop_model.py", "ref_harness.py"]

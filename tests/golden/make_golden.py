@@ -177,6 +177,41 @@ def make_dealer_vectors() -> dict:
     return {"source": "oracle.keys.dealer_keygen keys, reference PaillierSharedKey arithmetic", "keys": out}
 
 
+DIGEST_SPECS = [
+    # name (same keys as dealer_vectors.json: same seeds), key_length, parties, t, exact, seed, vectors
+    ("cfg1_k512_p3_t1", 512, 3, 1, False, 20261018, 160),
+    ("cfg2_k2048_p3_t1_exact", 2048, 3, 1, True, 20261019, 96),
+    ("cfg2_k2048_p3_t1_real", 2048, 3, 1, False, 20261020, 96),
+    ("cfg3_k2048_p5_t2_exact", 2048, 5, 2, True, 20261021, 64),
+    ("cfg4_k4096_p3_t1_exact", 4096, 3, 1, True, 20261022, 8),
+]
+
+
+from digests import digest_inputs, sha  # noqa: E402  (tests/golden/digests.py)
+
+
+def make_dealer_digests() -> dict:
+    """More vectors per key than dealer_vectors.json holds in full (more than one warp of the
+    2048/4096-bit kernels): inputs are regenerated from the seed, the reference's outputs are
+    recorded as SHA-256 digests (ciphertext, every party's partial decryption, plaintext)."""
+    out = {}
+    for name, kl, parties, t, exact, seed, nvec in DIGEST_SPECS:
+        print("digest set", name, nvec, flush=True)
+        dk = okeys.dealer_keygen(kl, parties, t, seed=seed, exact=exact)
+        refs = {pid: ref_key_from_oracle_key(k) for pid, k in dk.keys.items()}
+        scheme = _Scheme(dk.n)
+        rows = []
+        for m, r in digest_inputs(dk.n, seed, nvec):
+            c = encrypt_raw(dk.n, m, r)
+            partials = {pid: int(key.partial_decrypt(PaillierCiphertext(c, scheme))) for pid, key in refs.items()}
+            plain = int(refs[1].decrypt(dict(partials)))
+            assert plain == m
+            rows.append({"c": sha(c), "partials": {str(pid): sha(v) for pid, v in partials.items()}, "plaintext": sha(plain)})
+        out[name] = {"key_length": kl, "parties": parties, "t": t, "exact": exact, "seed": seed, "n": hex(dk.n), "vectors": rows}
+    return {"source": "oracle.keys.dealer_keygen keys, reference PaillierSharedKey arithmetic, SHA-256 of the values",
+            "keys": out}
+
+
 def make_biprime_vectors() -> dict:
     """Run the reference's v calculation and verdict on synthetic candidates: real biprimes (must
     pass) and random products of non-primes (must fail)."""
@@ -239,7 +274,10 @@ def main() -> None:
         ("fixture_vectors.json", make_fixture_vectors),
         ("biprime_vectors.json", make_biprime_vectors),
         ("dealer_vectors.json", make_dealer_vectors),
+        ("dealer_digests.json", make_dealer_digests),
     ]:
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         data = fn()
         path = os.path.join(HERE, name)
         with open(path, "w") as fh:

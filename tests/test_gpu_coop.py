@@ -185,3 +185,40 @@ def test_coop_and_wave_kernels_agree_on_a_mixed_batch(native):
     # spot check against CPython
     idx = [int(i) for i in np.flatnonzero(unit)[:4]]
     assert [limbs_to_ints(out_a[i : i + 1])[0] for i in idx] == [pow(vals[i], e, n2) for i in idx]
+
+
+@pytest.mark.parametrize("coop", [True, False])
+def test_rows_not_below_the_modulus_are_flagged(native, coop):
+    """The limb API takes values < modulus; a row that fits the limb width but is >= N^2 must come
+    back with status 3 and a zero row, never as a silently wrong residue (both routes)."""
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+
+    rng = random.Random(31)
+    n = 1000003 * 999983
+    n2 = n * n
+    top = 1 << (32 * ((n2.bit_length() + 31) // 32))
+    for e in (65537, -65537):
+        vals = [rng.randrange(1, n2) for _ in range(40)]
+        vals = [v for v in vals if math.gcd(v, n) == 1]
+        bad = {2: n2, 5: n2 + 1, 9: top - 1}
+        for i, v in bad.items():
+            vals[i] = v
+        ctx = _ctx(native, n2, e, n, coop)
+        out, st = ctx.modexp_limbs(ints_to_limbs(vals, ctx.limbs))
+        ctx.close()
+        got = limbs_to_ints(out)
+        for i, v in enumerate(vals):
+            if i in bad:
+                assert st[i] == 3 and got[i] == 0
+            else:
+                assert st[i] == 0 and got[i] == pow(v, e, n2)
+    # generic odd modulus (direct kernel)
+    from protocols.distributed_keygen_b200 import ModexpContext
+
+    m = rng.getrandbits(200) | 1 | (1 << 199)
+    ctx = ModexpContext(m, 12345)
+    vals = [rng.randrange(m) for _ in range(10)] + [m, m + 7]
+    out, st = ctx.modexp_limbs(ints_to_limbs(vals, ctx.limbs))
+    ctx.close()
+    assert list(st) == [0] * 10 + [3, 3]
+    assert limbs_to_ints(out)[:10] == [pow(v, 12345, m) for v in vals[:10]]

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def tagged(v: int):
-    if v.bit_length() < 64:
+    if v.bit_length() <= 64:   # native msgpack integers cover [0, 2^64) (uint64, 0xcf)
         return v
     return {"type": "int", "data": v.to_bytes((v.bit_length() + 8) // 8, "little", signed=True)}
 
@@ -107,3 +107,9 @@ def test_decode_errors():
     good = generic_message([2**100])
     with pytest.raises(ValueError):
         wire.unpack_partial_decryption_message(good + b"\x00", 8)
+    # an array header that promises more elements than the message has bytes (peer input) must not
+    # size an allocation: ValueError, not MemoryError
+    with pytest.raises(ValueError):
+        wire.decode_int_rows(b"\xdd\xff\xff\xff\xff", 8)
+    with pytest.raises(ValueError):
+        wire.decode_int_rows(b"\xdc\xff\xff\x01", 8)
