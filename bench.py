@@ -4,6 +4,8 @@ Benchmark of the threshold-Paillier hot path on B200 (BASELINE.json metric: thre
 decrypts/sec at 2048-bit N).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python bench.py --split --gpus N [--config cfg2|cfg3] [--total T]   # ONE process, one fixed batch
+                                                                        # sharded over N GPUs (strong scaling)
 
 Workload (BASELINE.json configs[1]): 3 parties, corruption threshold t=1, key_length 2048
 (exact 2048-bit N, 4096-bit N^2; synthetic dealer-generated key and uniformly random ciphertext
@@ -14,9 +16,13 @@ negative => batched modular inversion) + one share combination  (prod mod N^2, L
 reference (paillier_shared_key.py:52-127, distributed_keygen.py:430-517).
 
 Printed JSON line (rank 0): `value` = threshold decrypts/s with inputs resident in HBM, `e2e` =
-the same through the public host-buffer API (pinned host -> device copies and result read-back
-inside the timed region), `roofline` = the modexp kernel against the measured integer-multiplier
-peak, `cpu_baseline` = GMP mpz_powm (the function gmpy2.powmod wraps) on all host cores.
+the same through the public host-buffer call a user makes (`ThresholdContext.decrypt_limbs` = C ABI
+dkg_threshold_decrypt_batch: ciphertexts uploaded ONCE from pinned host memory, d+1 partial
+decryptions + combination on the device, plaintexts and all partials read back, inside the timed
+region), `e2e.python_int_api` = the same through Python ints, `roofline` = the modexp kernel against
+the measured integer-multiplier peak, `cpu_baseline` = GMP mpz_powm (the function gmpy2.powmod
+wraps) on all host cores, `latency` = ms per call at B = 1 / 32 / 1024 / 16384 (cooperative
+warp-per-ciphertext kernels) next to GMP, `secondary` = the other BASELINE.json configurations.
 Multi-GPU: one process per GPU (torchrun), ciphertext batches sharded by index, no data-path
 collective; only a barrier and a max-over-ranks of the elapsed time go through NCCL.
 """
@@ -38,6 +44,12 @@ METRIC = "threshold decrypts/sec (2048-bit N)"
 UNIT = "decrypts/s"
 KEY_NAME = "cfg2_k2048_p3_t1_exact"
 WORKLOAD = "cfg2: 3 parties t=1 key_length=2048 (exact 2048-bit N): 3 partial decryptions + share combination per ciphertext"
+
+
+def shared_config(dk) -> dict:
+    """The `config` object both arms print (the driver compares them)."""
+    return {"workload": WORKLOAD, "parties": dk.parties, "threshold": dk.t, "modulus_bits": dk.n.bit_length(),
+            "key": KEY_NAME}
 
 
 class KeyData:
@@ -218,6 +230,282 @@ def cpu_baseline(dk, cores: int, sample: int, seed: int, cpython: bool = True) -
     return out
 
 
+def gpu_keys(dk, device: int = 0):
+    """The engine-side key objects of parties 1..d+1 for a KeyData."""
+    import math
+
+    import protocols.distributed_keygen_b200 as eng
+
+    n_fac = math.factorial(dk.parties)
+    out = {}
+    for pid in range(1, 2 * dk.t + 2):
+        share = eng.IntegerShares({pid: dk.shares[pid]}, 2 * dk.t, n_fac * n_fac, dk.parties)
+        out[pid] = eng.PaillierSharedKey(dk.n, dk.t, pid, share, dk.theta, device=device)
+    return out
+
+
+def _best_ms(fn, reps: int) -> float:
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best * 1e3
+
+
+def latency_block(dk, cores: int) -> dict:
+    """ms per call (host buffers, copies included) of ONE party's partial decryption as a function of
+    the batch size -- the reference decrypts one ciphertext per `_decrypt_raw` call and ten in its own
+    sequence test -- next to GMP mpz_powm on all host cores for the same rows.  Small batches take the
+    cooperative warp-per-ciphertext kernels (csrc/dkg_coop.cuh), large ones the thread-per-ciphertext
+    wave kernels; the switch is automatic."""
+    import protocols.distributed_keygen_b200 as eng
+    from oracle import gmp
+    from protocols.distributed_keygen_b200.limbs import limbs_to_ints
+
+    keys = gpu_keys(dk)
+    n2 = dk.n * dk.n
+    rows_out = []
+    exps = {pid: k.partial_decrypt_exponent() for pid, k in keys.items()}
+    pid = next((p for p, e in exps.items() if e < 0), 1)   # the costlier sign
+    e = exps[pid]
+    ctx = keys[pid]._modexp_ctx()
+    L2 = ctx.limbs
+    mod = gmp.int_to_limbs(n2, L2)
+    el = gmp.int_to_limbs(abs(e), (abs(e).bit_length() + 31) // 32)
+    for B in (1, 32, 1024, 16384):
+        cts = random_units(B, n2, L2, 4000 + B)
+        res = [None]
+
+        def call():
+            res[0] = ctx.modexp_limbs(cts)
+
+        gpu_ms = _best_ms(call, 3 if B <= 1024 else 2)
+        sample = cts[: min(B, 4 * cores)]
+        want, secs = gmp.powm_batch_threads(sample, mod, el, e < 0, cores)
+        assert (res[0][0][: len(sample)] == want).all(), "latency block: GPU and GMP disagree"
+        cpu_ms = secs / -(-len(sample) // cores) * -(-B // cores) * 1e3
+        rows_out.append({"batch": B, "gpu_ms": round(gpu_ms, 3), "gmp_ms": round(cpu_ms, 3),
+                         "gpu_per_s": round(B / gpu_ms * 1e3, 1)})
+    # full threshold decryption of ONE ciphertext through the reference-shaped scalar calls
+    c = limbs_to_ints(random_units(1, n2, L2, 77))[0]
+
+    def one():
+        parts = {p: k.partial_decrypt(c) for p, k in keys.items()}
+        # (a random unit is not an encryption: skip the combination's divisibility check)
+        return parts
+
+    one_ms = _best_ms(one, 3)
+    for k in keys.values():
+        k.close()
+    return {"op": "partial_decrypt, party %d (exponent sign %s)" % (pid, "-" if e < 0 else "+"), "cpu_cores": cores,
+            "rows": rows_out, "three_partials_one_ciphertext_ms": round(one_ms, 3),
+            "note": "gmp_ms = measured on a sample of min(B, 4*cores) rows with all cores, scaled to ceil(B/cores) rounds"}
+
+
+def secondary_block(peak_tmacs: float) -> list:
+    """The BASELINE.json configurations that are not the headline, one entry each, device-resident
+    timing with CUDA events (one launch of one kernel wave unless noted), spot-checked against CPython
+    pow.  canonical_frac / executed_frac = canonical and really executed wide-MACs per
+    second over the measured IMAD peak of this run."""
+    import random
+
+    import numpy as np
+    import torch
+
+    import protocols.distributed_keygen_b200 as eng
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+
+    with open(os.path.join(ROOT, "tests", "golden", "dealer_vectors.json")) as fh:
+        dv = json.load(fh)["keys"]
+    out = []
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def time_ctx(label, modulus, exponent, root, waves=1):
+        ctx = eng.ModexpContext(modulus, exponent, root=root)
+        info = ctx.info()
+        B = waves * info["ctas"] * info["warps_per_cta"] * 32
+        host = random_units(B, modulus, ctx.limbs, 7)
+        d_in = torch.from_numpy(host.view(np.int32)).cuda()
+        d_out = torch.empty_like(d_in)
+        d_st = torch.empty(B, dtype=torch.uint8, device="cuda")
+        ctx.modexp_device(d_in.data_ptr(), d_out.data_ptr(), d_st.data_ptr(), B, stream)   # warm-up (same size: same route)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.modexp_device(d_in.data_ptr(), d_out.data_ptr(), d_st.data_ptr(), B, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        got = d_out[B - 1 :].cpu().numpy().view(np.uint32)
+        base = limbs_to_ints(host[B - 1 :])[0]
+        assert limbs_to_ints(got)[0] == pow(base, exponent, modulus), label
+        ebits = abs(exponent).bit_length()
+        canon = B * canonical_modexp_macs(ebits, ctx.limbs) / (ms * 1e-3) / 1e12
+        execd = B * actual_modexp_macs(info) / (ms * 1e-3) / 1e12
+        ctx.close()
+        line = {"config": label, "count": B, "ms": round(ms, 2), "per_s": round(B / ms * 1e3, 1),
+                "modulus_bits": modulus.bit_length(), "exponent_bits": ebits * (1 if exponent > 0 else -1),
+                "kernel": ("modexp_nsq_kernel<%d,%d>" % (info["pair_K"], info["pair_M"])) if info["pair_arithmetic"]
+                else ("modexp_fixed_kernel<%d,%d>" % (info["K"], info["M"])),
+                "canonical_frac": round(canon / peak_tmacs, 3), "executed_frac": round(execd / peak_tmacs, 3)}
+        out.append(line)
+        return line
+
+    # cfg2 with a reference-shaped key (N = 2050..2052 bits, 129-limb N^2)
+    real = KeyData(dv["cfg2_k2048_p3_t1_real"]["key"])
+    kreal = gpu_keys(real)
+    for pid in (1, 2):
+        time_ctx(f"cfg2 reference-shaped key, partial decrypt party {pid}", real.n * real.n, kreal[pid].partial_decrypt_exponent(), real.n)
+    # cfg3: 5 parties t=2: full threshold decryption (5 partials + combination) and combine-only
+    c3 = KeyData(dv["cfg3_k2048_p5_t2_exact"]["key"])
+    k3 = gpu_keys(c3)
+    ex3 = {p: k.partial_decrypt_exponent() for p, k in k3.items()}
+    per = [time_ctx(f"cfg3 (5 parties t=2), partial decrypt party {p}", c3.n * c3.n, ex3[p], c3.n) for p in sorted(ex3)]
+    comb = k3[1]._combine_ctx()
+    Bc = 1 << 17
+    parts = torch.from_numpy(random_units(5 * Bc, c3.n * c3.n, comb.n2_limbs, 3).view(np.int32)).cuda()
+    d_o = torch.empty((Bc, comb.n_limbs), dtype=torch.int32, device="cuda")
+    d_s = torch.empty(Bc, dtype=torch.uint8, device="cuda")
+    comb.combine_device(parts.data_ptr(), d_o.data_ptr(), d_s.data_ptr(), Bc, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    comb.combine_device(parts.data_ptr(), d_o.data_ptr(), d_s.data_ptr(), Bc, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    cms = e0.elapsed_time(e1)
+    comb_macs = (4 * (2 * 128 * 128 + 128) + 2 * 64 * 64 + 64) * 1.0
+    out.append({"config": "cfg3 combine-only, 5 partials (device-resident)", "count": Bc, "ms": round(cms, 3),
+                "per_s": round(Bc / cms * 1e3, 1), "canonical_frac": round(Bc * comb_macs / (cms * 1e-3) / 1e12 / peak_tmacs, 3)})
+    step_ms = sum(p["ms"] for p in per) + cms * per[0]["count"] / Bc
+    out.append({"config": "cfg3 threshold decrypt (5 partial decryptions + combination, sum of the launches above)",
+                "count": per[0]["count"], "ms": round(step_ms, 2), "per_s": round(per[0]["count"] / step_ms * 1e3, 1)})
+    for k in list(kreal.values()) + list(k3.values()):
+        k.close()
+    # cfg4: key_length 4096; encryption randomness at 2048 and 4096
+    c4 = KeyData(dv["cfg4_k4096_p3_t1_exact"]["key"])
+    k4 = gpu_keys(c4)
+    time_ctx("cfg4 key_length 4096, partial decrypt party 1", c4.n * c4.n, k4[1].partial_decrypt_exponent(), c4.n)
+    time_ctx("cfg4 key_length 4096, r^N", c4.n * c4.n, c4.n, c4.n)
+    for k in k4.values():
+        k.close()
+    c2 = KeyData(dv[KEY_NAME]["key"])
+    time_ctx("cfg2 key_length 2048, r^N (encryption randomness)", c2.n * c2.n, c2.n, c2.n)
+    # cfg5: biprimality-test batch sweep, host buffers end to end, party 1 exponent, 40 bases per candidate
+    rng = random.Random(5)
+    sweep = []
+    for C in (1, 4, 16, 64, 256, 1024, 4096, 16384, 65536):
+        base_c = min(C, 64)
+        moduli, exps = [], []
+        for _ in range(base_c):
+            ps = [(rng.getrandbits(1024) | (1 << 1023) | 3) if i == 0 else ((rng.getrandbits(1024) | (1 << 1023)) & ~3) for i in range(3)]
+            qs = [(rng.getrandbits(1024) | (1 << 1023) | 3) if i == 0 else ((rng.getrandbits(1024) | (1 << 1023)) & ~3) for i in range(3)]
+            n = sum(ps) * sum(qs)
+            moduli.append(n)
+            exps.append((n - ps[0] - qs[0] + 1) // 4)
+        L = 65
+        reps = -(-C // base_c)
+        m_arr = np.tile(ints_to_limbs(moduli, L), (reps, 1))[:C]
+        e_arr = np.tile(ints_to_limbs(exps, L), (reps, 1))[:C]
+        bases = random_units(C * 40, 1 << 2049, L, 11).reshape(C, 40, L)    # < 2^2048 <= N
+        eng.modexp_grouped_limbs(m_arr[:1], e_arr[:1], bases[:1])
+        t0 = time.perf_counter()
+        res = eng.modexp_grouped_limbs(m_arr, e_arr, bases)
+        secs = time.perf_counter() - t0
+        b0 = limbs_to_ints(bases[C - 1, 39:40])[0]
+        assert limbs_to_ints(res[C - 1, 39:40])[0] == pow(b0, exps[(C - 1) % base_c], moduli[(C - 1) % base_c])
+        canon = C * 40 * canonical_modexp_macs(2046, 64) / secs / 1e12
+        sweep.append({"candidates": C, "modexps": 40 * C, "ms": round(secs * 1e3, 2), "modexps_per_s": round(40 * C / secs, 1),
+                      "canonical_frac": round(canon / peak_tmacs, 3)})
+    out.append({"config": "cfg5 biprimality-test v_1 batch, 2050-bit candidates, 40 bases each, host buffers end to end "
+                          "(<= 16384 modexps: cooperative kernel, above: thread-per-operand kernel)", "sweep": sweep})
+    return out
+
+
+def run_split(args) -> None:
+    """ONE process, ONE fixed batch sharded by index over --gpus devices through the public call
+    (C ABI dkg_threshold_*): strong scaling with the host gather, as SURVEY.md section 8(e) and
+    BASELINE config 3 ("10M ciphertexts across 8 GPUs") describe.  Host buffers are page-locked."""
+    import numpy as np
+
+    import protocols.distributed_keygen_b200 as eng
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkgmod
+    from protocols.distributed_keygen_b200.limbs import limbs_to_ints
+
+    with open(os.path.join(ROOT, "tests", "golden", "dealer_vectors.json")) as fh:
+        dv = json.load(fh)["keys"]
+    name = KEY_NAME if args.config == "cfg2" else "cfg3_k2048_p5_t2_exact"
+    dk = KeyData(dv[name]["key"])
+    devices = list(range(args.gpus))
+    keys = gpu_keys(dk)
+    ctx = dkgmod.threshold_context(keys, devices)
+    info = keys[1]._modexp_ctx().info()
+    total = args.total or 2 * len(devices) * info["ctas"] * info["warps_per_cta"] * 32
+    n2 = dk.n * dk.n
+    cts = random_units(total, n2, ctx.n2_limbs, 4242)
+    plain = np.zeros((total, ctx.n_limbs), dtype=np.uint32)
+    status = np.zeros(total, dtype=np.uint8)
+    from protocols.distributed_keygen_b200 import _native
+
+    lines = {}
+    with eng.pinned(cts, plain, status):
+        def decrypt():
+            _native.check(_native.lib.dkg_threshold_decrypt_batch(ctx._h, cts.ctypes.data, plain.ctypes.data, None, status.ctypes.data, total))
+
+        warm = min(total, 4096 * len(devices))
+        _native.check(_native.lib.dkg_threshold_decrypt_batch(ctx._h, cts.ctypes.data, plain.ctypes.data, None, status.ctypes.data, warm))
+        launches0 = eng.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            decrypt()
+        secs = (time.perf_counter() - t0) / args.steps
+        launches = eng.launch_count() - launches0
+        lines["decrypt"] = secs
+    # spot check: partials of a few rows against CPython, plaintext against the combination formula
+    theta_inv = pow(dk.theta, -1, dk.n)
+    exps = {p: k.partial_decrypt_exponent() for p, k in keys.items()}
+    for i in (0, total // 2, total - 1):
+        c = limbs_to_ints(cts[i : i + 1])[0]
+        x = 1
+        for p, e in exps.items():
+            x = x * (pow(pow(c, -1, n2), -e, n2) if e < 0 else pow(c, e, n2)) % n2
+        want = ((x - 1) // dk.n) * theta_inv % dk.n if (x - 1) % dk.n == 0 else None
+        got = limbs_to_ints(plain[i : i + 1])[0]
+        assert (want is None and status[i] == 2) or (want == got and status[i] == 0), f"split mode: row {i} differs"
+    # combine-only on a slice (partials produced by the per-party call)
+    sub = min(total, 1 << 20)
+    parts = np.zeros((ctx.shares, sub, ctx.n2_limbs), dtype=np.uint32)
+    for p in range(ctx.shares):
+        parts[p], _ = ctx.partial_decrypt_limbs(p + 1, cts[:sub])
+    plain2 = np.zeros((sub, ctx.n_limbs), dtype=np.uint32)
+    st2 = np.zeros(sub, dtype=np.uint8)
+    with eng.pinned(parts, plain2, st2):
+        _native.check(_native.lib.dkg_threshold_combine_batch(ctx._h, parts.ctypes.data, plain2.ctypes.data, st2.ctypes.data, min(sub, 4096)))
+        t0 = time.perf_counter()
+        _native.check(_native.lib.dkg_threshold_combine_batch(ctx._h, parts.ctypes.data, plain2.ctypes.data, st2.ctypes.data, sub))
+        comb_secs = time.perf_counter() - t0
+    assert np.array_equal(plain2, plain[:sub]) and np.array_equal(st2, status[:sub])
+    ctx.close()
+    line = {
+        "metric": METRIC if args.config == "cfg2" else "threshold decrypts/sec (2048-bit N, 5 parties t=2)",
+        "value": total / secs, "unit": UNIT, "n_gpus": len(devices), "steps": args.steps, "warmup": 1,
+        "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 limbs (exact integer)", "data": "synthetic", "mode": "split: one process, one host array in, host gather out",
+        "config": {"workload": ("cfg3: 5 parties t=2 key_length=2048: 5 partial decryptions + share combination per ciphertext"
+                                if args.config == "cfg3" else WORKLOAD),
+                   "parties": dk.parties, "threshold": dk.t, "modulus_bits": dk.n.bit_length(), "key": name},
+        "details": {"ciphertexts": total, "devices": devices, "shares": ctx.shares},
+        "e2e": {"value": total / secs, "unit": UNIT, "h2d_bytes_per_step": total * ctx.n2_limbs * 4,
+                "d2h_bytes_per_step": total * (ctx.n_limbs * 4 + 1)},
+        "combine_only": {"value": sub / comb_secs, "unit": "combines/s", "count": sub,
+                         "h2d_bytes": sub * ctx.shares * ctx.n2_limbs * 4, "note": "partials start on the host (page-locked): PCIe-bound"},
+        "gpu_launches": int(launches),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -236,7 +524,7 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": sample},
+        "data": "synthetic", "config": shared_config(dk), "details": {"sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": vals[-1]["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -255,10 +543,17 @@ def main() -> None:
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the latency block and the secondary configurations")
+    ap.add_argument("--split", action="store_true", help="one process, one fixed batch sharded over --gpus devices (strong scaling)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"], help="--split: which BASELINE.json configuration")
+    ap.add_argument("--total", type=int, default=0, help="--split: ciphertexts in the batch (0 = two waves per GPU)")
     args = ap.parse_args()
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.split and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_split(args)
         return
 
     import numpy as np
@@ -374,19 +669,22 @@ def main() -> None:
         assert (x - 1) % dk.n == 0, "combined value minus one not divisible by N"
         assert limbs_to_ints(plain_host[i : i + 1])[0] == ((x - 1) // dk.n) * theta_inv % dk.n, "combine mismatch"
 
-    # ---- end to end through the host-buffer API ------------------------------------------------
+    # ---- end to end through the public host-buffer call ------------------------------------------
     e2e = None
     if not args.no_e2e:
+        from protocols.distributed_keygen_b200 import distributed_keygen as dkgmod
+
+        tctx = dkgmod.threshold_context(keys, [local_rank])
         pinned_partials = torch.empty((shares, B, L2), dtype=torch.int32).pin_memory()
+        pinned_plain = torch.empty((B, Ln), dtype=torch.int32).pin_memory()
+        pinned_status = torch.empty(B, dtype=torch.uint8).pin_memory()
         np_cts = pinned_cts.numpy().view(np.uint32)
-        np_partials = pinned_partials.numpy().view(np.uint32)
 
         def e2e_step():
-            for s, pid in enumerate(range(1, shares + 1)):
-                out, status = keys[pid].partial_decrypt_limbs(np_cts)   # H2D + kernel + D2H
-                np_partials[s] = out
-            plain_out, cstatus = keys[1].decrypt_limbs(np_partials)     # H2D + kernel + D2H
-            return plain_out, cstatus
+            # one call: H2D of the ciphertexts (once), 3 partial decryptions + combination, D2H of
+            # the plaintexts, every party's partials and the status bytes
+            _native.check(_native.lib.dkg_threshold_decrypt_batch(
+                tctx._h, np_cts.ctypes.data, pinned_plain.data_ptr(), pinned_partials.data_ptr(), pinned_status.data_ptr(), B))
 
         e2e_steps = max(1, min(args.steps, 3))
         e2e_step()
@@ -400,10 +698,25 @@ def main() -> None:
         if distributed:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_secs = float(t.item())
-        h2d = shares * B * L2 * 4 + shares * B * L2 * 4
-        d2h = shares * (B * L2 * 4 + B) + B * Ln * 4 + B
+        assert not pinned_status.numpy().any()
+        assert np.array_equal(pinned_partials.numpy().view(np.uint32)[:, : min(B, 4096)], part_host[:, : min(B, 4096)])
+        assert np.array_equal(pinned_plain.numpy().view(np.uint32), plain_host)
+        h2d = B * L2 * 4
+        d2h = shares * B * L2 * 4 + B * Ln * 4 + B
         e2e = {"value": world * B * e2e_steps / e2e_secs, "unit": UNIT, "steps": e2e_steps,
-               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world}
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "call": "ThresholdContext.decrypt_limbs / dkg_threshold_decrypt_batch (ciphertexts uploaded once; plaintexts + all partials + status read back)"}
+        tctx.close()
+        if rank == 0:
+            # the same through Python ints (the reference-shaped signatures: lists of int in and out)
+            k_int = min(B, 16384)
+            ints = limbs_to_ints(host_cts[:k_int])
+            t0 = time.perf_counter()
+            got_int = dkgmod.decrypt_sequence_local(keys, ints)
+            py_secs = time.perf_counter() - t0
+            assert got_int[:8] == limbs_to_ints(plain_host[:8])
+            e2e["python_int_api"] = {"value": k_int / py_secs, "unit": UNIT, "batch": k_int,
+                                     "call": "distributed_keygen.decrypt_sequence_local (Python ints in and out, per-party calls)"}
 
     # ---- true encryptions through the same kernels: decrypt(encrypt(m)) == m -------------------
     import random
@@ -436,9 +749,9 @@ def main() -> None:
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (exact integer)",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD, "ciphertexts_per_gpu_per_step": B, "parties": dk.parties,
-                "threshold": dk.t, "modulus_bits": dk.n.bit_length(), "n2_limbs": L2,
+            "config": shared_config(dk),
+            "details": {
+                "ciphertexts_per_gpu_per_step": B, "n2_limbs": L2,
                 "exponent_bits": [abs(exps[p]).bit_length() * (1 if exps[p] > 0 else -1) for p in sorted(exps)],
                 "kernel_shape": info, "parallelism": f"index-sharded x{world}, no collective",
                 "cache": "inputs+outputs per step (%.0f MB) larger than L2" % ((shares + 1) * B * L2 * 4 / 1e6),
@@ -473,6 +786,11 @@ def main() -> None:
         cores = os.cpu_count() or 1
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(dk, cores, args.cpu_sample or max(cores * 96, 256), 5)
+            if not args.no_secondary:
+                for key in keys.values():
+                    key.close()
+                line["latency"] = latency_block(dk, cores)
+                line["secondary"] = secondary_block(peak)
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
