@@ -614,13 +614,28 @@ __global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p
           }
         }
         __syncwarp();
-        copy(A, entry((int)(p.ops[0] & 0xffu)), 2 * Lc);
+        // constant-time table access: scan every entry (and the Montgomery one for digit 0) under
+        // a mask instead of reading entry `di` (see modexp_nsq_kernel)
+        auto ct_select = [&](uint32_t* dst, uint32_t di) {
+          const uint32_t m0 = 0u - (uint32_t)(di == 0xfeu);
+          for (int l = lane; l < 2 * Lc; l += 32) {
+            uint32_t acc = cONEA[l] & m0;
+            for (int k = 0; k < tn; ++k) acc |= entry(k)[l] & (0u - (uint32_t)((uint32_t)k == di));
+            dst[l] = acc;
+          }
+        };
+        if (p.ct_table) ct_select(A, p.ops[0] & 0xffu);
+        else copy(A, entry((int)(p.ops[0] & 0xffu)), 2 * Lc);
         __syncwarp();
         for (int t = 1; t < p.nops; ++t) {
           const uint32_t op = p.ops[t];
           for (uint32_t q = op >> 8; q > 0; --q) pair_sqr<K>(w, pr);
           const uint32_t di = op & 0xffu;
-          if (di == 0xfeu) pair_mul<K>(w, pr, sONEA, sONEB);
+          if (p.ct_table) {
+            ct_select(C, di);
+            __syncwarp();
+            pair_mul<K>(w, pr, sC, sD);
+          } else if (di == 0xfeu) pair_mul<K>(w, pr, sONEA, sONEB);
           else if (di != 0xffu) {
             copy(C, entry((int)di), 2 * Lc);
             __syncwarp();

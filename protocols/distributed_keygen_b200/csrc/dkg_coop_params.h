@@ -27,6 +27,7 @@ struct CoopNsqParams {
   const uint32_t* consts;
   const uint32_t* ops;        // operation list of the context (see ModexpParams)
   int nops, tab_entries, table_odd;
+  int ct_table;               // masked scan of the whole table per multiplication (fixed windows only)
   uint32_t* scratch;          // per-warp window table, (tab_entries + 1) * 2 * Lc words
   unsigned long long scratch_per_warp;
   unsigned int* counter;

@@ -268,7 +268,12 @@ long env_long(const char* name, long dflt) {
 // Process-wide settings, initialised from the environment once (DKG_COOP=0 disables,
 // DKG_COOP_MAX / DKG_COOP_GROUPED_MAX set the limits) and changed through dkg_config_set; a
 // fixed-modulus context takes its limit when it is created.
-std::atomic<long> g_coop_max{-1}, g_coop_grouped_max{-1};
+std::atomic<long> g_coop_max{-1}, g_coop_grouped_max{-1}, g_ct_table{-1};
+bool ct_table_setting() {
+  long v = g_ct_table.load();
+  if (v < 0) { v = env_long("DKG_CT_TABLE", 0) != 0 ? 1 : 0; g_ct_table.store(v); }
+  return v != 0;
+}
 size_t coop_limit(std::atomic<long>& slot, const char* env_name, long dflt) {
   long v = slot.load();
   if (v < 0) {
@@ -317,6 +322,7 @@ struct dkg_modexp_ctx {
   dkg::CoopPlanTable cfull{}, clow{};
   bool use_nsq = true;             // knobs read once, when the context is created
   bool use_batch_inverse = true;
+  bool ct_table = false;           // constant-time table access (masked scan of all entries)
 };
 
 namespace {
@@ -330,6 +336,23 @@ int choose_window(int ebits, int max_w = 6) {
   long best_cost = -1;
   for (int w = 1; w <= max_w; ++w) {
     long cost = ((1L << w) - 2) + (ebits + w - 1) / w;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
+  }
+  return best;
+}
+
+// Window width under constant-time table access: every multiplication scans all 2^w entries
+// (~0.034 of a multiplication's time per entry at 2048-bit N: 560 B per thread against the L2/HBM
+// share of a thread), so narrower windows win: cost = 2^w - 2 + ceil(E/w) * (1 + 0.034 * 2^w).
+int choose_window_ct(int ebits) {
+  if (const char* f = getenv("DKG_FORCE_WINDOW")) {
+    int w = atoi(f);
+    if (w >= 1 && w <= 7) return w;
+  }
+  int best = 1;
+  double best_cost = -1;
+  for (int w = 1; w <= 7; ++w) {
+    const double cost = (double)((1L << w) - 2) + (double)((ebits + w - 1) / w) * (1.0 + 0.034 * (double)(1L << w));
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
   }
   return best;
@@ -498,6 +521,7 @@ int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d
   dkg::CoopNsqParams q{};
   q.pairs_in = pairs; q.pairs_out = pairs; q.status = d_status; q.count = count; q.nb = ctx->cnb; q.negative = ctx->negative;
   q.consts = ctx->d_cconsts; q.ops = ctx->d_ops; q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd;
+  q.ct_table = ctx->ct_table ? 1 : 0;
   q.scratch = d->scratch; q.scratch_per_warp = per_warp; q.counter = d->counter; q.full = ctx->cfull; q.low = ctx->clow;
   const size_t smem = ((size_t)dkg::kCoopNsqConsts + (size_t)dkg::kCoopNsqWarpBufs * warps) * Lc * 4;
   CUDA_TRY(dkg::launch_coop_nsq(ctx->cK, q, ctas, warps, smem, stream));
@@ -566,7 +590,7 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::NsqParams q{};
   q.pairs_in = pairs; q.pairs_out = pairs; q.count = count; q.consts = ctx->d_nconsts; q.ops = ctx->d_ops;
-  q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
+  q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd; q.ct_table = ctx->ct_table ? 1 : 0; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
   q.scratch_q_offset = ctx->nscratch_q_offset; q.counter = d->counter;
   ctx->nsq_kernel<<<ctas, ctx->nwarps * 32, ctx->nsmem, stream>>>(q);
   dkg::NsqIoParams x = e;
@@ -617,6 +641,7 @@ int dkg_config_set(const char* key, long value) {
   const std::string k(key);
   if (k == "coop_max") { coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault); g_coop_max.store(value); return DKG_OK; }
   if (k == "coop_grouped_max") { g_coop_grouped_max.store(value); return DKG_OK; }
+  if (k == "ct_table") { g_ct_table.store(value ? 1 : 0); return DKG_OK; }
   return fail(DKG_ERR_INVALID, "unknown configuration key");
 }
 int dkg_config_get(const char* key, long* value) {
@@ -624,6 +649,7 @@ int dkg_config_get(const char* key, long* value) {
   const std::string k(key);
   if (k == "coop_max") { *value = (long)coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault); return DKG_OK; }
   if (k == "coop_grouped_max") { *value = (long)coop_limit(g_coop_grouped_max, "DKG_COOP_GROUPED_MAX", kCoopGroupedMaxDefault); return DKG_OK; }
+  if (k == "ct_table") { *value = ct_table_setting() ? 1 : 0; return DKG_OK; }
   return fail(DKG_ERR_INVALID, "unknown configuration key");
 }
 
@@ -675,12 +701,13 @@ int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, co
   // windows (DKG_SLIDING_WINDOW=1) save 23 % of the multiplications (~1.5 % of the run time in the
   // pair arithmetic) at the price of an exponent-dependent operation list, as in mpz_powm.
   std::vector<uint32_t> ops;
-  if (const char* sw = getenv("DKG_SLIDING_WINDOW"); sw && atoi(sw) != 0) {
+  ctx->ct_table = ct_table_setting();
+  if (const char* sw = getenv("DKG_SLIDING_WINDOW"); sw && atoi(sw) != 0 && !ctx->ct_table) {
     ctx->wbits = choose_sliding_window(ctx->ebits);
     ops = sliding_window_ops(exponent, ctx->ebits, ctx->wbits, &ctx->tab_entries, &ctx->nmul);
     ctx->table_odd = 1;
   } else {
-    ctx->wbits = choose_window(ctx->ebits, 7);
+    ctx->wbits = ctx->ct_table ? choose_window_ct(ctx->ebits) : choose_window(ctx->ebits, 7);
     const int ndigits = (ctx->ebits + ctx->wbits - 1) / ctx->wbits;
     for (int t = 0; t < ndigits; ++t) {
       const int lowbit = ctx->wbits * (ndigits - 1 - t);

@@ -193,8 +193,34 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
           for (int v = 0; v < LV; ++v) { da[(size_t)v * 32] = Aw[v * 32 + lane]; db[(size_t)v * 32] = Bw[v * 32 + lane]; }
         }
       }
+      // Constant-time table access (p.ct_table, fixed windows only): instead of reading entry
+      // `idx`, scan ALL entries (and the Montgomery one, digit 0) in a fixed order and keep the
+      // wanted one under a mask, into the spare slot after the table: the addresses touched no
+      // longer depend on the exponent's digits.
+      auto ct_select = [&](uint32_t idx) {
+        V* da = tab_a(tn); V* db = tab_b(tn);
+        const uint32_t m0 = 0u - (uint32_t)(idx == 0xfeu);
+        for (int v = 0; v < LV; ++v) {
+          uint32_t aa[VW], bb[VW], tt[VW];
+          unpack(ONEAr[(size_t)v * 32], aa); unpack(ONEBr[(size_t)v * 32], bb);
+#pragma unroll
+          for (int q = 0; q < VW; ++q) { aa[q] &= m0; bb[q] &= m0; }
+          for (int k = 0; k < tn; ++k) {
+            const uint32_t mk = 0u - (uint32_t)((uint32_t)k == idx);
+            unpack(tab_a(k)[(size_t)v * 32], tt);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) aa[q] |= tt[q] & mk;
+            unpack(tab_b(k)[(size_t)v * 32], tt);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) bb[q] |= tt[q] & mk;
+          }
+          V oa, ob; pack(oa, aa); pack(ob, bb);
+          da[(size_t)v * 32] = oa; db[(size_t)v * 32] = ob;
+        }
+      };
       {
-        const int k0 = (int)(p.ops[0] & 0xffu);
+        int k0 = (int)(p.ops[0] & 0xffu);
+        if (p.ct_table) { ct_select((uint32_t)k0); k0 = tn; }
         const V* sa = tab_a(k0); const V* sb = tab_b(k0);
         for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = sa[(size_t)v * 32]; Bw[v * 32 + lane] = sb[(size_t)v * 32]; }
       }
@@ -202,7 +228,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
         const uint32_t op = p.ops[t];
         for (uint32_t s = op >> 8; s > 0; --s) pair_sqr();
         const uint32_t idx = op & 0xffu;
-        if (idx == 0xfeu) pair_mul(ONEAr, ONEBr);
+        if (p.ct_table) { ct_select(idx); pair_mul(tab_a(tn), tab_b(tn)); }
+        else if (idx == 0xfeu) pair_mul(ONEAr, ONEBr);
         else if (idx != 0xffu) pair_mul(tab_a((int)idx), tab_b((int)idx));
       }
     }

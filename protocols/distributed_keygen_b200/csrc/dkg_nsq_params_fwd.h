@@ -15,6 +15,7 @@ struct NsqParams {
   const uint32_t* consts;
   const uint32_t* ops;        // operation list, see ModexpParams
   int nops, tab_entries, table_odd;
+  int ct_table;               // masked scan of the whole table per multiplication (fixed windows only)
   uint32_t* scratch;
   unsigned long long scratch_per_warp;   // in uint32
   unsigned long long scratch_q_offset;

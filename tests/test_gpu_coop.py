@@ -222,3 +222,30 @@ def test_rows_not_below_the_modulus_are_flagged(native, coop):
     ctx.close()
     assert list(st) == [0] * 10 + [3, 3]
     assert limbs_to_ints(out)[:10] == [pow(v, 12345, m) for v in vals[:10]]
+
+
+@pytest.mark.parametrize("coop", [True, False])
+def test_constant_time_table_access_mode(native, coop):
+    """config "ct_table" (env DKG_CT_TABLE=1): every multiplication scans the whole window table
+    under a mask instead of indexing it with the exponent digit; same results, narrower windows."""
+    rng = random.Random(41)
+    native.config_set("ct_table", 1)
+    try:
+        for bits in (67, 515, 2051):
+            p = rng.getrandbits(bits // 2) | 1 | (1 << (bits // 2 - 1))
+            q = rng.getrandbits(bits - bits // 2) | 1 | (1 << (bits - bits // 2 - 1))
+            n = p * q
+            n2 = n * n
+            for sign in (1, -1):
+                ebits = 2 * bits + 60 if bits < 2000 else 700
+                e = sign * (rng.getrandbits(ebits) | (1 << (ebits - 1)))
+                # digits 0 inside the exponent exercise the masked Montgomery one
+                e = sign * (abs(e) & ~(0xFFFFF << 40))
+                bases = [b for b in (rng.randrange(1, n2) for _ in range(12)) if math.gcd(b, n) == 1]
+                ctx = _ctx(native, n2, e, n, coop)
+                info = ctx.info()
+                assert info["pair_arithmetic"] == 1 and info["window_bits"] <= 5
+                assert ctx.modexp(bases) == [pow(b, e, n2) for b in bases], (bits, sign, coop)
+                ctx.close()
+    finally:
+        native.config_set("ct_table", 0)
