@@ -254,6 +254,17 @@ def _best_ms(fn, reps: int) -> float:
     return best * 1e3
 
 
+def cpu_baseline_rows(rows, modulus: int, exponent: int, cores: int):
+    """GMP mpz_powm (+ mpz_invert) over `rows` on `cores` pthreads: (results, seconds).  CPU-baseline
+    leg of the latency block (and its checker)."""
+    from oracle import gmp
+
+    L = rows.shape[1]
+    mag = abs(exponent)
+    return gmp.powm_batch_threads(rows, gmp.int_to_limbs(modulus, L), gmp.int_to_limbs(mag, (mag.bit_length() + 31) // 32),
+                                  exponent < 0, cores)
+
+
 def latency_block(dk, cores: int) -> dict:
     """ms per call (host buffers, copies included) of ONE party's partial decryption as a function of
     the batch size -- the reference decrypts one ciphertext per `_decrypt_raw` call and ten in its own
@@ -261,7 +272,6 @@ def latency_block(dk, cores: int) -> dict:
     cooperative warp-per-ciphertext kernels (csrc/dkg_coop.cuh), large ones the thread-per-ciphertext
     wave kernels; the switch is automatic."""
     import protocols.distributed_keygen_b200 as eng
-    from oracle import gmp
     from protocols.distributed_keygen_b200.limbs import limbs_to_ints
 
     keys = gpu_keys(dk)
@@ -272,8 +282,6 @@ def latency_block(dk, cores: int) -> dict:
     e = exps[pid]
     ctx = keys[pid]._modexp_ctx()
     L2 = ctx.limbs
-    mod = gmp.int_to_limbs(n2, L2)
-    el = gmp.int_to_limbs(abs(e), (abs(e).bit_length() + 31) // 32)
     for B in (1, 32, 1024, 16384):
         cts = random_units(B, n2, L2, 4000 + B)
         res = [None]
@@ -283,7 +291,7 @@ def latency_block(dk, cores: int) -> dict:
 
         gpu_ms = _best_ms(call, 3 if B <= 1024 else 2)
         sample = cts[: min(B, 4 * cores)]
-        want, secs = gmp.powm_batch_threads(sample, mod, el, e < 0, cores)
+        want, secs = cpu_baseline_rows(sample, n2, e, cores)
         assert (res[0][0][: len(sample)] == want).all(), "latency block: GPU and GMP disagree"
         cpu_ms = secs / -(-len(sample) // cores) * -(-B // cores) * 1e3
         rows_out.append({"batch": B, "gpu_ms": round(gpu_ms, 3), "gmp_ms": round(cpu_ms, 3),

@@ -18,31 +18,11 @@ from typing import Iterable, Mapping, Sequence
 
 import numpy as np
 
-from .engine import biprime_v_batch_limbs, biprime_verdict, modexp_grouped, small_prime_sieve
+from .engine import biprime_v_batch_limbs, biprime_verdict, small_prime_sieve
 from .limbs import ints_to_limbs, limbs_for_bits, limbs_to_ints
 from .paillier_shared_key import PaillierSharedKey
 
 JACOBI_CORRECTION_FACTOR = 4  # distributed_keygen.py:60
-
-
-def jacobi_symbol(a: int, n: int) -> int:
-    """Jacobi symbol (a/n), n odd and positive: what ``sympy.jacobi_symbol`` returns at ``:1089``.
-    Host-side filter in front of the GPU batch (binary algorithm)."""
-    if n <= 0 or n % 2 == 0:
-        raise ValueError("n should be an odd positive integer")
-    a %= n
-    result = 1
-    while a:
-        tz = (a & -a).bit_length() - 1
-        if tz:
-            a >>= tz
-            if tz & 1 and n & 7 in (3, 5):
-                result = -result
-        a, n = n, a
-        if a & 3 == 3 and n & 3 == 3:
-            result = -result
-        a %= n
-    return result if n == 1 else 0
 
 
 def biprime_exponent(index: int, modulus: int, p_i: int, q_i: int) -> int:
@@ -50,18 +30,6 @@ def biprime_exponent(index: int, modulus: int, p_i: int, q_i: int) -> int:
     if index == 1:
         return (modulus - p_i - q_i + 1) // 4
     return (p_i + q_i) // 4
-
-
-def _select_g(g_values: Iterable[int], modulus: int, correct_param_biprime: int) -> list[int]:
-    """``:1084-1091``: the first ``correct_param_biprime`` g's whose Jacobi symbol is +1."""
-    picked: list[int] = []
-    for g in g_values:
-        if len(picked) == correct_param_biprime:
-            break
-        if jacobi_symbol(g, modulus) != 1:
-            continue
-        picked.append(g)
-    return picked
 
 
 def biprime_test_v_calculation_batch(
@@ -77,23 +45,26 @@ def biprime_test_v_calculation_batch(
         return []
     moduli = [c[1] for c in candidates]
     exps = [biprime_exponent(index, n, p_i, q_i) for (_, n, p_i, q_i) in candidates]
-    ng = len(candidates[0][0])
-    if ng > 0 and all(len(c[0]) == ng for c in candidates) and min(exps) >= 0:
-        # everything on the device: Jacobi filter, selection, grouped modexp (one call)
-        limbs = limbs_for_bits(max(n.bit_length() for n in moduli))
-        exp_limbs = limbs_for_bits(max(max(e.bit_length() for e in exps), 1))
-        flat = [g % n for (gs, n, _, _) in candidates for g in gs]
-        g_arr = ints_to_limbs(flat, limbs).reshape(len(candidates), ng, limbs)
-        v, count = biprime_v_batch_limbs(
-            ints_to_limbs(moduli, limbs), ints_to_limbs(exps, exp_limbs), g_arr,
-            min(correct_param_biprime, ng), device,
-        )
-        c_eff = v.shape[1]
-        vals = limbs_to_ints(v.reshape(-1, limbs))
-        return [vals[i * c_eff : i * c_eff + int(count[i])] for i in range(len(candidates))]
-    # ragged g lists: filter on the host, then one grouped modexp
-    bases = [_select_g(g, n, correct_param_biprime) for (g, n, _, _) in candidates]
-    return modexp_grouped(moduli, exps, bases, device)
+    if min(exps) < 0:
+        raise ValueError("negative biprimality-test exponent (p_i + q_i or N - p_i - q_i + 1 must be >= 0)")
+    # everything on the device: Jacobi filter (sympy.jacobi_symbol at :1089), selection of the first
+    # `correct_param_biprime` usable g's, grouped modexp -- one call.  Ragged g lists are padded with
+    # zeros: (0 / N) = 0 is never selected.
+    ng = max(max(len(c[0]) for c in candidates), 1)
+    limbs = limbs_for_bits(max(n.bit_length() for n in moduli))
+    exp_limbs = limbs_for_bits(max(max(e.bit_length() for e in exps), 1))
+    flat: list[int] = []
+    for gs, n, _, _ in candidates:
+        flat.extend(g % n for g in gs)
+        flat.extend([0] * (ng - len(gs)))
+    g_arr = ints_to_limbs(flat, limbs).reshape(len(candidates), ng, limbs)
+    v, count = biprime_v_batch_limbs(
+        ints_to_limbs(moduli, limbs), ints_to_limbs(exps, exp_limbs), g_arr,
+        max(1, min(correct_param_biprime, ng)), device,
+    )
+    c_eff = v.shape[1]
+    vals = limbs_to_ints(v.reshape(-1, limbs))
+    return [vals[i * c_eff : i * c_eff + min(int(count[i]), correct_param_biprime)] for i in range(len(candidates))]
 
 
 def biprime_test_v_calculation(

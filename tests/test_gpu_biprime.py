@@ -157,3 +157,23 @@ def test_biprime_verdict_on_gpu(biprime_vectors):
     # a candidate with too few usable g's fails
     short = {p: [v_by_party[p][0][:5]] for p in v_by_party}
     assert dkg.biprime_test_with_v_i_batch(short, [cands[0][1]], correct) == [False]
+
+
+def test_ragged_g_lists_stay_on_the_gpu(biprime_vectors):
+    """Candidates with different numbers of g values (and one with none) in one call: padded on the
+    way in, Jacobi filter and selection on the device; equals the oracle's restatement of
+    distributed_keygen.py:1080-1099 per candidate."""
+    from oracle import paillier_oracle as po
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+
+    cases = [c for c in biprime_vectors["cases"] if c["key_length"] <= 512]
+    batch, want = [], []
+    for k, case in enumerate(cases):
+        n = _h(case["n"])
+        g_values = [_h(g) for g in case["g_values"]][: max(0, len(case["g_values"]) - 13 * k)]
+        p_i, q_i = _h(case["p_shares"][1]), _h(case["q_shares"][1])
+        batch.append((g_values, n, p_i, q_i))
+        want.append(po.biprime_v_calculation(g_values, 2, n, p_i, q_i, 20))
+    batch.append(([], _h(cases[0]["n"]), _h(cases[0]["p_shares"][1]), _h(cases[0]["q_shares"][1])))
+    want.append([])
+    assert dkg.biprime_test_v_calculation_batch(batch, 2, 20) == want

@@ -87,17 +87,15 @@ def test_jacobi_and_biprime_host_logic(biprime_vectors):
     from protocols.distributed_keygen_b200 import distributed_keygen as dkg
 
     rng = random.Random(3)
-    for _ in range(300):
+    for _ in range(300):   # the oracle's Jacobi symbol (the product computes it on the GPU only)
         n = rng.getrandbits(rng.choice([8, 40, 200])) | 1
         a = rng.getrandbits(210)
-        assert dkg.jacobi_symbol(a, n) == sympy.jacobi_symbol(a, n) == po.jacobi(a, n)
-    with pytest.raises(ValueError):
-        dkg.jacobi_symbol(3, 10)
+        assert sympy.jacobi_symbol(a, n) == po.jacobi(a, n)
+    assert not hasattr(dkg, "jacobi_symbol") and not hasattr(dkg, "_select_g"), "no host-side filter in the product"
     for case in biprime_vectors["cases"]:
         n = int(case["n"], 16)
         g_values = [int(g, 16) for g in case["g_values"]]
         correct = case["correct_param_biprime"]
-        assert dkg._select_g(g_values, n, correct) == po.biprime_select_g(g_values, n, correct)
         for i in range(1, case["parties"] + 1):
             p_i, q_i = int(case["p_shares"][i - 1], 16), int(case["q_shares"][i - 1], 16)
             assert dkg.biprime_exponent(i, n, p_i, q_i) == po.biprime_exponent(i, n, p_i, q_i)
@@ -146,7 +144,7 @@ def test_key_blob_reader_on_reference_fixtures(fixture_vectors):
 
 def test_oracle_is_test_infrastructure_only():
     """Nothing under the product package imports oracle/, and bench.py touches it only inside the
-    CPU-baseline / reference-arm helpers (oracle_key, cpu_baseline)."""
+    CPU-baseline / reference-arm helpers (oracle_key, cpu_baseline*)."""
     import ast
     import pathlib
 
@@ -168,6 +166,6 @@ def test_oracle_is_test_infrastructure_only():
     tree = ast.parse(bench.read_text())
     allowed = set()
     for node in tree.body:
-        if isinstance(node, ast.FunctionDef) and node.name in ("oracle_key", "cpu_baseline"):
+        if isinstance(node, ast.FunctionDef) and (node.name == "oracle_key" or node.name.startswith("cpu_baseline")):
             allowed.update(range(node.lineno, node.end_lineno + 1))
     assert all(line in allowed for line in oracle_imports(bench)), "bench.py uses the oracle outside the CPU-baseline leg"
