@@ -305,10 +305,21 @@ def latency_block(dk, cores: int) -> dict:
         return parts
 
     one_ms = _best_ms(one, 3)
+    # ... and through the one-call threshold path (all parties' exponentiations in one cooperative
+    # launch, combination on the device)
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkgmod
+
+    tctx = dkgmod.threshold_context(keys, [0])
+    fused = {}
+    for B in (1, 32, 1024):
+        cts = random_units(B, n2, L2, 5000 + B)
+        fused[str(B)] = round(_best_ms(lambda: tctx.decrypt_limbs(cts, want_partials=True), 3), 3)
+    tctx.close()
     for k in keys.values():
         k.close()
     return {"op": "partial_decrypt, party %d (exponent sign %s)" % (pid, "-" if e < 0 else "+"), "cpu_cores": cores,
             "rows": rows_out, "three_partials_one_ciphertext_ms": round(one_ms, 3),
+            "threshold_decrypt_call_ms_by_batch": fused,
             "note": "gmp_ms = measured on a sample of min(B, 4*cores) rows with all cores, scaled to ceil(B/cores) rounds"}
 
 

@@ -560,13 +560,17 @@ __global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p
     unsigned long long idx = 0;
     if (lane == 0) idx = atomicAdd(p.counter, 1u);
     idx = __shfl_sync(kCoopFull, idx, 0);
-    if (idx >= p.count) break;
-    copy(A, p.pairs_in + idx * (unsigned long long)(2 * Lc), 2 * Lc);   // A | B contiguous
+    if (idx >= p.count * (unsigned long long)p.nparties) break;
+    const int party = (int)(idx / p.count);
+    const unsigned long long ct = idx % p.count;
+    const uint32_t* ops = p.ops[party];
+    const int nops = p.nops[party], tn = p.tab_entries[party], table_odd = p.table_odd[party], negative = p.negative[party];
+    copy(A, p.pairs_in + ct * (unsigned long long)(2 * Lc), 2 * Lc);   // A | B contiguous
     __syncwarp();
     bool ok = true;
-    if (p.negative) { copy(I0, A, Lc); __syncwarp(); }
+    if (negative) { copy(I0, A, Lc); __syncwarp(); }
     pair_mul<K>(w, pr, sR2A, sR2B);             // into the Montgomery domain: x R
-    if (p.negative) {
+    if (negative) {
       // x^-1 = y0 (2 - x y0) with y0 = (x mod N)^-1 taken modulo N: one Newton step modulo N^2
       copy(XA, A, 2 * Lc); __syncwarp();        // XA | XB
       ok = mod_inverse<K>(w, sI0, sI0);
@@ -590,15 +594,14 @@ __global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p
       }
     }
     if (ok) {
-      if (p.nops == 0) {
+      if (nops == 0) {
         copy(A, cONEA, 2 * Lc); __syncwarp();   // ONEA | ONEB contiguous
       } else {
-        const int tn = p.tab_entries;
         auto entry = [&](int k) -> uint32_t* { return tab + (size_t)k * 2 * Lc; };
         copy(entry(0), A, 2 * Lc);
         if (tn > 1) {
           int src = 0;
-          if (p.table_odd) {                    // odd powers: multiply by c^2, kept after the last entry
+          if (table_odd) {                      // odd powers: multiply by c^2, kept after the last entry
             pair_sqr<K>(w, pr);
             copy(entry(tn), A, 2 * Lc);
             __syncwarp();
@@ -624,11 +627,11 @@ __global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p
             dst[l] = acc;
           }
         };
-        if (p.ct_table) ct_select(A, p.ops[0] & 0xffu);
-        else copy(A, entry((int)(p.ops[0] & 0xffu)), 2 * Lc);
+        if (p.ct_table) ct_select(A, ops[0] & 0xffu);
+        else copy(A, entry((int)(ops[0] & 0xffu)), 2 * Lc);
         __syncwarp();
-        for (int t = 1; t < p.nops; ++t) {
-          const uint32_t op = p.ops[t];
+        for (int t = 1; t < nops; ++t) {
+          const uint32_t op = ops[t];
           for (uint32_t q = op >> 8; q > 0; --q) pair_sqr<K>(w, pr);
           const uint32_t di = op & 0xffu;
           if (p.ct_table) {

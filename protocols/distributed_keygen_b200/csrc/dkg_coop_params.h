@@ -16,19 +16,23 @@ struct CoopPlanTable {
   int32_t ndiag;          // lanes 0..ndiag-1 are primaries
 };
 
+constexpr int kCoopMaxParties = 8;
+
 struct CoopNsqParams {
   const uint32_t* pairs_in;   // [count][2][Lc] plain pairs (c mod N, (c div N) * R mod N), R = 2^(32 Lc)
-  uint32_t* pairs_out;        // [count][2][Lc] plain pairs of the result
-  uint8_t* status;            // [count] or null: 1 = base not invertible (negative exponent only)
-  unsigned long long count;
+  uint32_t* pairs_out;        // [nparties][count][2][Lc] plain pairs of the results
+  uint8_t* status;            // [nparties][count] or null: 1 = base not invertible (negative exponent only)
+  unsigned long long count;   // ciphertexts; instance j = (party j / count, ciphertext j % count)
   int nb;                     // blocks per component; Lc = nb * K
-  int negative;
   // N | NI (-N^-1 mod R) | DNEG (-R mod N) | R2A | R2B | ONEA | ONEB | TWOA | TWOB | PLAIN1 | ZERO
   const uint32_t* consts;
-  const uint32_t* ops;        // operation list of the context (see ModexpParams)
-  int nops, tab_entries, table_odd;
+  // per party (all parties of one key share N; a plain context is the one-party case): the
+  // operation list of its exponent (see ModexpParams), sign, table size
+  int nparties;
+  const uint32_t* ops[kCoopMaxParties];
+  int nops[kCoopMaxParties], tab_entries[kCoopMaxParties], table_odd[kCoopMaxParties], negative[kCoopMaxParties];
   int ct_table;               // masked scan of the whole table per multiplication (fixed windows only)
-  uint32_t* scratch;          // per-warp window table, (tab_entries + 1) * 2 * Lc words
+  uint32_t* scratch;          // per-warp window table, (max tab_entries + 1) * 2 * Lc words
   unsigned long long scratch_per_warp;
   unsigned int* counter;
   CoopPlanTable full, low;

@@ -406,7 +406,8 @@ std::vector<uint32_t> sliding_window_ops(const uint32_t* e, int ebits, int w, in
 }
 
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
-                      size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows = nullptr, int m_limbs = 0);
+                      size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows = nullptr, int m_limbs = 0,
+                      const unsigned int** redo_flag = nullptr);
 int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status, size_t count,
                        cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs);
 
@@ -448,10 +449,12 @@ int launch_modexp_inner(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* 
   if (count == 0) return DKG_OK;
   DeviceState* d = ctx->dev;
   CUDA_TRY(cudaSetDevice(d->device));
+  const unsigned int* redo_flag = nullptr;
   if (ctx->nsq && d_final_mul == nullptr && ctx->use_nsq) {
     bool handled = false;
-    int rc0 = launch_modexp_nsq(ctx, d_bases, d_out, d_status, count, stream, &handled);
-    if (rc0 != DKG_OK || handled) return rc0;
+    int rc0 = launch_modexp_nsq(ctx, d_bases, d_out, d_status, count, stream, &handled, nullptr, 0, &redo_flag);
+    if (rc0 != DKG_OK || (handled && redo_flag == nullptr)) return rc0;
+    // handled with a device-side "redo" flag: fall through to the direct kernel, predicated on it
   }
   const unsigned long long ngroups = (count + 31) / 32;
   const int total_warps = ctx->ctas * ctx->warps;
@@ -461,8 +464,9 @@ int launch_modexp_inner(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* 
   if (rc != DKG_OK) return rc;
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::ModexpParams p{};
-  if (ctx->negative && ctx->inv_kernel != nullptr && ngroups >= 2 && ctx->use_batch_inverse) {
+  if (ctx->negative && ctx->inv_kernel != nullptr && ngroups >= 2 && ctx->use_batch_inverse && redo_flag == nullptr) {
     // Montgomery's trick along chains of ~32 groups: one binary-GCD inversion per chain lane
+    // (the predicated redo of a pair-path call inverts per element instead: exact status)
     const size_t gwords = (size_t)ctx->Lp * 32;
     const int nchain = inversion_chain_warps(d, ctx, ngroups);
     const int chain_len = (int)((ngroups + nchain - 1) / nchain);
@@ -484,6 +488,7 @@ int launch_modexp_inner(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* 
   p.consts = ctx->d_consts; p.ops = ctx->d_ops; p.nops = ctx->nops; p.tab_entries = ctx->tab_entries; p.table_odd = ctx->table_odd;
   p.negative = ctx->negative; p.n0inv = ctx->n0inv; p.scratch = d->scratch;
   p.scratch_per_warp = ctx->scratch_per_warp; p.scratch_q_offset = ctx->scratch_q_offset; p.counter = d->counter; p.final_mul = d_final_mul;
+  p.run_if = redo_flag;
   ctx->kernel<<<ctas, ctx->warps * 32, ctx->smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -499,48 +504,69 @@ void coop_grid(const DeviceState* d, int K, bool pair_kernel, size_t count, int*
   *ctas = (int)std::min<size_t>((count + *warps - 1) / *warps, (size_t)d->sm_count * std::max(1, maxw / *warps));
 }
 
-// Small batches modulo N^2: entry -> cooperative pair exponentiation (a warp per ciphertext,
-// negative exponents inverted in the kernel, per-element status) -> exit.
-int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status, size_t count,
-                       cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs) {
+// Small batches modulo N^2: entry -> cooperative pair exponentiation (a warp per (party,
+// ciphertext), negative exponents inverted in the kernel, per-element status) -> exit.  `parties`
+// are contexts of ONE key (same N, hence the same cooperative constants and plans): their partial
+// decryptions of the same ciphertexts go out as [nparties][count][limbs] in one launch sequence,
+// so that a threshold decryption of a few ciphertexts costs one exponentiation's latency, not d+1.
+int launch_modexp_coop_parties(dkg_modexp_ctx* const* parties, int nparties, const uint32_t* d_bases, uint32_t* d_out,
+                               uint8_t* d_status, size_t count, cudaStream_t stream, const uint32_t* d_mrows, int m_limbs) {
+  dkg_modexp_ctx* ctx = parties[0];
   DeviceState* d = ctx->dev;
   const int Lc = ctx->cLc;
+  const size_t instances = count * (size_t)nparties;
   int ctas = 1, warps = 1;
-  coop_grid(d, ctx->cK, true, count, &ctas, &warps);
-  const size_t per_warp = ((size_t)ctx->tab_entries + 1) * 2 * Lc;
-  const size_t pair_words = count * (size_t)(2 * Lc);
+  coop_grid(d, ctx->cK, true, instances, &ctas, &warps);
+  size_t per_warp = 0;
+  for (int p = 0; p < nparties; ++p) per_warp = std::max(per_warp, ((size_t)parties[p]->tab_entries + 1) * 2 * Lc);
+  const size_t pair_words = (count + instances) * (size_t)(2 * Lc);
   int rc = ensure_scratch(d, (size_t)ctas * warps * per_warp);
   if (rc == DKG_OK) rc = ensure_aux(d, pair_words);
   if (rc != DKG_OK) return rc;
-  uint32_t* pairs = d->aux;
+  uint32_t* pairs_in = d->aux;
+  uint32_t* pairs_out = d->aux + count * (size_t)(2 * Lc);
   dkg::NsqIoParams e{};
-  e.in = d_bases; e.out = pairs; e.count = count; e.io_limbs = ctx->limbs; e.Lp = Lc; e.consts = ctx->d_cio; e.n0inv = ctx->n_n0inv;
+  e.in = d_bases; e.out = pairs_in; e.count = count; e.io_limbs = ctx->limbs; e.Lp = Lc; e.consts = ctx->d_cio; e.n0inv = ctx->n_n0inv;
   e.mrows = nullptr; e.m_limbs = 0;
   dkg::nsq_entry_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(e);
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
   dkg::CoopNsqParams q{};
-  q.pairs_in = pairs; q.pairs_out = pairs; q.status = d_status; q.count = count; q.nb = ctx->cnb; q.negative = ctx->negative;
-  q.consts = ctx->d_cconsts; q.ops = ctx->d_ops; q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd;
+  q.pairs_in = pairs_in; q.pairs_out = pairs_out; q.status = d_status; q.count = count; q.nb = ctx->cnb;
+  q.consts = ctx->d_cconsts; q.nparties = nparties;
+  for (int p = 0; p < nparties; ++p) {
+    q.ops[p] = parties[p]->d_ops; q.nops[p] = parties[p]->nops; q.tab_entries[p] = parties[p]->tab_entries;
+    q.table_odd[p] = parties[p]->table_odd; q.negative[p] = parties[p]->negative;
+  }
   q.ct_table = ctx->ct_table ? 1 : 0;
   q.scratch = d->scratch; q.scratch_per_warp = per_warp; q.counter = d->counter; q.full = ctx->cfull; q.low = ctx->clow;
   const size_t smem = ((size_t)dkg::kCoopNsqConsts + (size_t)dkg::kCoopNsqWarpBufs * warps) * Lc * 4;
   CUDA_TRY(dkg::launch_coop_nsq(ctx->cK, q, ctas, warps, smem, stream));
   dkg::NsqIoParams x = e;
-  x.in = pairs; x.out = d_out; x.mrows = d_mrows; x.m_limbs = m_limbs;
-  dkg::nsq_exit_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(x);
+  x.in = pairs_out; x.out = d_out; x.count = instances; x.mrows = d_mrows; x.m_limbs = m_limbs;
+  dkg::nsq_exit_kernel<<<(unsigned)((instances + 63) / 64), 64, 0, stream>>>(x);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(3);
-  *handled = true;
   return DKG_OK;
+}
+
+int launch_modexp_coop(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status, size_t count,
+                       cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs) {
+  int rc = launch_modexp_coop_parties(&ctx, 1, d_bases, d_out, d_status, count, stream, d_mrows, m_limbs);
+  *handled = rc == DKG_OK;
+  return rc;
 }
 
 // Modulus N^2 with known N: [batched inversion ->] entry (pairs) -> pair exponentiation -> exit.
 // Falls back to the direct kernel (handled = false) when a chain of the batched inversion hit a
 // non-unit, so that the per-element status comes out exact.
 int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_out, uint8_t* d_status,
-                      size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs) {
+                      size_t count, cudaStream_t stream, bool* handled, const uint32_t* d_mrows, int m_limbs,
+                      const unsigned int** redo_flag) {
   DeviceState* d = ctx->dev;
   *handled = false;
+  const unsigned int* no_flag = nullptr;
+  if (redo_flag == nullptr) redo_flag = &no_flag;
+  *redo_flag = nullptr;
   if (ctx->coop && count <= ctx->coop_max) return launch_modexp_coop(ctx, d_bases, d_out, d_status, count, stream, handled, d_mrows, m_limbs);
   const unsigned long long ngroups = (count + 31) / 32;
   const int Lp = ctx->nLp;
@@ -567,10 +593,10 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
     ctx->inv_kernel<<<blocks, ctx->inv_warps * 32, ctx->inv_smem, stream>>>(b);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
-    unsigned int any_bad = 0;
-    CUDA_TRY(cudaMemcpyAsync(&any_bad, b.any_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    if (any_bad) return DKG_OK;  // not handled: the direct path reports the status per element
+    // No host round trip: if a chain met a non-unit (any_bad != 0, decided on the device) the pair
+    // path's results of this call are discarded and the direct kernel -- launched below on the same
+    // stream, predicated on that flag -- redoes the call with the exact per-element status.
+    *redo_flag = b.any_bad;
     src = b.plain_out;
     inv_off = inv_words;
   } else {
@@ -1583,9 +1609,20 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
       if (job.mode == 1) {
         rc = launch_modexp(dv.parties[job.party], B.in, B.part, B.st, nullptr, rows, s);
       } else {
-        if (job.mode == 0)
-          for (int p = 0; p < S && rc == DKG_OK; ++p)
-            rc = launch_modexp(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, nullptr, rows, s);
+        if (job.mode == 0) {
+          // a few ciphertexts: every party's exponentiation in ONE cooperative launch (one warp per
+          // (party, ciphertext)); otherwise one wave launch per party
+          bool fused = S <= dkg::kCoopMaxParties;
+          for (int p = 0; p < S; ++p) fused = fused && dv.parties[p]->coop && dv.parties[p]->use_nsq && rows * (size_t)S <= dv.parties[p]->coop_max;
+          if (fused) {
+            rc = launch_modexp_coop_parties(dv.parties.data(), S, B.in, B.part, B.st, rows, s, nullptr, 0);
+            for (int p = 0; p < S && rc == DKG_OK; ++p)
+              rc = launch_range_check(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, rows, s);
+          } else {
+            for (int p = 0; p < S && rc == DKG_OK; ++p)
+              rc = launch_modexp(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, nullptr, rows, s);
+          }
+        }
         if (rc == DKG_OK) rc = launch_combine(dv.combine, B.part, B.out, B.st + (size_t)S * rows, rows, s);
       }
       if (rc != DKG_OK) { *err = g_err; break; }

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
   io.nis = (uint32_t)__cvta_generic_to_shared(NIs);
   io.Qg = Qg + lane; io.Y = nullptr;
 
-  const unsigned long long ngroups = (p.count + 31ull) / 32ull;
+  const unsigned long long ngroups = (p.run_if != nullptr && *p.run_if == 0u) ? 0ull : (p.count + 31ull) / 32ull;
   for (;;) {
     unsigned int g = 0;
     if (lane == 0) g = atomicAdd(p.counter, 1u);

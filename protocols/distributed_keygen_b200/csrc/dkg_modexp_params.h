@@ -50,6 +50,9 @@ struct ModexpParams {
   unsigned long long scratch_per_warp;  // in uint32
   unsigned long long scratch_q_offset;  // offset (uint32) of the quotient-block area inside a warp's scratch
   unsigned int* counter;   // work-group ticket
+  // optional: run only if *run_if != 0 (the device-side decision "the batched inversion of the
+  // pair path met a non-unit: redo the call here, with exact per-element status"); null = always
+  const unsigned int* run_if;
   // optional per-element plain multiplier applied at the end (encryption: 1 + m N), or null
   const uint32_t* final_mul;  // [count][in_limbs]
   // batched inversion results (negative exponents): c^-1 * R per group in lane layout, and one

@@ -75,9 +75,12 @@ def test_coop_matches_thread_per_operand_kernel_and_golden(native, dealer_vector
                 b.close()
 
 
-def test_coop_negative_exponent_status_per_element(native):
+@pytest.mark.parametrize("coop", [True, False])
+def test_negative_exponent_status_per_element(native, coop):
     """Non-units under a negative exponent: status 1 on exactly those rows, zero rows, the others
-    correct (the reference raises ZeroDivisionError from mod_inv per ciphertext)."""
+    correct (the reference raises ZeroDivisionError from mod_inv per ciphertext).  Cooperative route:
+    per-instance inversion.  Thread-per-operand route: the batched inversion flags the chain on the
+    device and the predicated direct kernel redoes the call -- no host round trip in between."""
     from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
 
     rng = random.Random(11)
@@ -85,11 +88,11 @@ def test_coop_negative_exponent_status_per_element(native):
     n = p * q
     n2 = n * n
     e = -(rng.getrandbits(90) | 1)
-    bases = [rng.randrange(1, n2) for _ in range(20)]
-    bad = {3: p * 12345, 7: q * q * 5, 11: 0, 19: n}
+    bases = [rng.randrange(1, n2) for _ in range(200)]
+    bad = {3: p * 12345, 7: q * q * 5, 11: 0, 19: n, 150: p, 199: q * 77}
     for i, v in bad.items():
         bases[i] = v % n2
-    ctx = _ctx(native, n2, e, n, True)
+    ctx = _ctx(native, n2, e, n, coop)
     out, status = ctx.modexp_limbs(ints_to_limbs(bases, ctx.limbs))
     ctx.close()
     vals = limbs_to_ints(out)
@@ -99,7 +102,7 @@ def test_coop_negative_exponent_status_per_element(native):
         else:
             assert status[i] == 0 and vals[i] == pow(b, e, n2), i
     with pytest.raises(ZeroDivisionError):
-        c2 = _ctx(native, n2, e, n, True)
+        c2 = _ctx(native, n2, e, n, coop)
         try:
             c2.modexp(bases)
         finally:
