@@ -25,6 +25,20 @@ static cudaError_t launch_grouped_t(const CoopGroupedParams& p, int ctas, int wa
   return cudaGetLastError();
 }
 
+template <int K, int THREADS>
+static cudaError_t launch_combine_t(const CoopCombineParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
+  auto kernel = coop_combine_kernel<K, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<ctas, warps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_coop_combine(int K, const CoopCombineParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
+  if (K == 6) return launch_combine_t<6, 512>(p, ctas, warps, smem, stream);
+  if (K == 12) return launch_combine_t<12, 256>(p, ctas, warps, smem, stream);
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_coop_nsq(int K, const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream) {
   if (K == 6) return launch_nsq_t<6, 256>(p, ctas, warps, smem, stream);
   if (K == 12) return launch_nsq_t<12, 256>(p, ctas, warps, smem, stream);

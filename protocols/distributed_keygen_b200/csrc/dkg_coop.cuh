@@ -656,6 +656,109 @@ __global__ void __launch_bounds__(THREADS) coop_nsq_kernel(const CoopNsqParams p
   }
 }
 
+// ---- share combination, one ciphertext per warp -------------------------------------------------------
+// x = prod_j partial_j mod N^2 (Montgomery products on the plain inputs, one multiplication by
+// R^shares at the end); y = x - 1; N | y and u = y / N from ONE Montgomery reduction of y modulo N:
+// with q = y * (-N^-1) mod R,  (y + q N) / R = N  <=>  y = (R - q) N,  so u = R - q (u = 0: y = 0);
+// m = u * theta^-1 mod N.
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS) coop_combine_kernel(const CoopCombineParams p) {
+  using namespace coop;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* S = reinterpret_cast<uint32_t*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = p.nb, Lc = nb * K;
+  for (int i = threadIdx.x; i < kCoopCombineConsts * Lc; i += blockDim.x) S[i] = p.consts[i];
+  __syncthreads();
+  const sa c0 = saddr(S), LB = (uint32_t)(Lc * 4);
+  const sa sN2 = c0, sNI2 = c0 + LB, sRPOW = c0 + 2 * LB, sN = c0 + 3 * LB, sNIN = c0 + 4 * LB, sTHR = c0 + 5 * LB;
+  uint32_t* W = S + kCoopCombineConsts * Lc + (size_t)warp * kCoopCombineWarpBufs * Lc;
+  uint32_t *X = W, *Y = W + Lc;
+  const sa w0 = saddr(W);
+  const sa sX = w0, sY = w0 + LB, sT = w0 + 2 * LB, sU = w0 + 4 * LB;
+  Warp<K> w2;   // modulo N^2
+  w2.lane = lane; w2.nb = nb; w2.pf.load(p.full, lane); w2.pl.load(p.low, lane);
+  w2.N = sN2; w2.NI = sNI2; w2.T = sT;
+  Warp<K> w1 = w2;   // modulo N
+  w1.N = sN; w1.NI = sNIN;
+  uint32_t n2reg[K], nreg[K];
+  w2.load_block(n2reg, sN2);
+  w1.load_block(nreg, sN);
+
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(p.counter, 1u);
+    idx = __shfl_sync(kCoopFull, idx, 0);
+    if (idx >= p.count) break;
+    const uint32_t* row = p.partials + idx * (unsigned long long)p.l2;
+    for (int l = lane; l < Lc; l += 32) X[l] = l < p.l2 ? row[l] : 0u;
+    __syncwarp();
+    for (int s = 1; s < p.shares; ++s) {
+      row = p.partials + ((unsigned long long)s * p.count + idx) * (unsigned long long)p.l2;
+      for (int l = lane; l < Lc; l += 32) Y[l] = l < p.l2 ? row[l] : 0u;
+      __syncwarp();
+      montmul<K>(w2, sX, sX, sY, 0, 0);
+    }
+    montmul<K>(w2, sX, sX, sRPOW, 0, 0);         // plain product modulo N^2, < 2 N^2
+    uint32_t x[K], t[K], one[K];
+    w2.load_block(x, sX);
+    if (sub<K>(t, x, n2reg, lane, nb)) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = t[k];
+    }
+    bool bad = is_zero<K>(x);                    // x = 0: (0 - 1) % N != 0 in the reference
+#pragma unroll
+    for (int k = 0; k < K; ++k) one[k] = (lane == 0 && k == 0) ? 1u : 0u;
+    sub<K>(t, x, one, lane, nb);                 // y = x - 1
+    const bool y_zero = is_zero<K>(t);
+    // y as a 2nb-block number in the T | Q area (high half zero), then its Montgomery reduction mod N
+    if (lane < nb) sts<K>(sT + (uint32_t)(lane * K * 4), t);
+    else if (lane < 2 * nb) {
+      uint32_t z[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) z[k] = 0;
+      sts<K>(sT + (uint32_t)(lane * K * 4), z);
+    }
+    __syncwarp();
+    montmul<K>(w1, sU, 0, 0, 0, 0);              // U <- (y + q N) / R, q in w1.Q()
+    w1.load_block(x, sU);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) diff |= x[k] ^ nreg[k];
+    const bool is_n = __ballot_sync(kCoopFull, diff != 0) == 0u;
+    bad = bad || !(is_n || y_zero);
+    // u = R - q  (0 when y = 0)
+    uint32_t q[K], nq[K], zero[K];
+    w1.load_block(q, w1.Q());
+#pragma unroll
+    for (int k = 0; k < K; ++k) { nq[k] = lane < nb ? ~q[k] : 0u; zero[k] = 0; }
+    add<K>(t, nq, zero, 1u, lane, nb);
+    if (y_zero) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = 0;
+    }
+    w1.store_block(sU, t);
+    __syncwarp();
+    montmul<K>(w1, sU, sU, sTHR, 0, 0);          // u * theta^-1 mod N, < 2N
+    w1.load_block(x, sU);
+    if (sub<K>(t, x, nreg, lane, nb)) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = t[k];
+    }
+    if (bad) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = 0;
+    }
+    w1.store_block(sU, x);
+    __syncwarp();
+    uint32_t* o = p.out + idx * (unsigned long long)p.ln;
+    const uint32_t* U = W + 4 * Lc;
+    for (int l = lane; l < p.ln; l += 32) o[l] = U[l];
+    if (p.status != nullptr && lane == 0) p.status[idx] = bad ? 2 : 0;
+    __syncwarp();
+  }
+}
+
 // ---- grouped exponentiation (per-instance modulus and exponent), one instance per warp ---------------
 template <int K, int THREADS>
 __global__ void __launch_bounds__(THREADS) coop_grouped_kernel(const CoopGroupedParams p) {

@@ -40,6 +40,22 @@ struct CoopNsqParams {
 constexpr int kCoopNsqConsts = 11;
 constexpr int kCoopNsqWarpBufs = 14;   // numbers of nb*K limbs of shared memory per warp
 
+// Share combination (PaillierSharedKey.decrypt, paillier_shared_key.py:108-125), one ciphertext per warp.
+struct CoopCombineParams {
+  const uint32_t* partials;   // [shares][count][l2]
+  uint32_t* out;              // [count][ln]
+  uint8_t* status;            // [count] or null: 2 = (x - 1) not divisible by N
+  unsigned long long count;
+  int shares, l2, ln;
+  int nb;                     // Lc = nb * K limbs, R = 2^(32 Lc) >= 4 N^2
+  // N2 | NI2 (-N2^-1 mod R) | RPOW (R^shares mod N^2) | N | NIN (-N^-1 mod R) | THR (theta^-1 * R mod N); Lc limbs each
+  const uint32_t* consts;
+  unsigned int* counter;
+  CoopPlanTable full, low;
+};
+constexpr int kCoopCombineConsts = 6;
+constexpr int kCoopCombineWarpBufs = 5;   // X Y T Q U
+
 struct CoopGroupedParams {
   const uint32_t* moduli;   // [groups][limbs]
   const uint32_t* exps;     // [groups][exp_limbs]

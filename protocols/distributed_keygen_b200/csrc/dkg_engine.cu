@@ -80,6 +80,7 @@ void launch_group_setup(const GroupedParams& p, cudaStream_t stream);
 int coop_max_warps(int K, bool pair_kernel);
 cudaError_t launch_coop_nsq(int K, const CoopNsqParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
 cudaError_t launch_coop_grouped(int K, const CoopGroupedParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
+cudaError_t launch_coop_combine(int K, const CoopCombineParams& p, int ctas, int warps, size_t smem, cudaStream_t stream);
 }  // namespace dkg
 namespace {
 
@@ -1018,6 +1019,11 @@ struct dkg_combine_ctx {
   int ln = 0, l2 = 0, shares = 0;
   uint32_t n2_0inv = 0, n_0inv = 0;
   uint32_t* d_consts = nullptr;
+  // warp-per-ciphertext kernel (dkg_coop.cuh: coop_combine_kernel), used whenever N^2 fits its shapes
+  bool coop = false;
+  int cK = 0, cnb = 0;
+  uint32_t* d_cconsts = nullptr;
+  dkg::CoopPlanTable cfull{}, clow{};
 };
 
 namespace {
@@ -1025,6 +1031,20 @@ int launch_combine(dkg_combine_ctx* ctx, const uint32_t* d_partials, uint32_t* d
                    size_t count, cudaStream_t stream) {
   if (count == 0) return DKG_OK;
   CUDA_TRY(cudaSetDevice(ctx->dev->device));
+  if (ctx->coop) {
+    DeviceState* d = ctx->dev;
+    const int Lc = ctx->cK * ctx->cnb;
+    int ctas = 1, warps = 1;
+    coop_grid(d, ctx->cK, ctx->cK == 12, count, &ctas, &warps);
+    CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
+    dkg::CoopCombineParams q{};
+    q.partials = d_partials; q.out = d_out; q.status = d_status; q.count = count; q.shares = ctx->shares; q.l2 = ctx->l2;
+    q.ln = ctx->ln; q.nb = ctx->cnb; q.consts = ctx->d_cconsts; q.counter = d->counter; q.full = ctx->cfull; q.low = ctx->clow;
+    const size_t smem = ((size_t)dkg::kCoopCombineConsts + (size_t)dkg::kCoopCombineWarpBufs * warps) * Lc * 4;
+    CUDA_TRY(dkg::launch_coop_combine(ctx->cK, q, ctas, warps, smem, stream));
+    g_launches.fetch_add(1);
+    return DKG_OK;
+  }
   dkg::CombineParams p{};
   p.partials = d_partials; p.out = d_out; p.status = d_status; p.count = count; p.shares = ctx->shares;
   p.l2 = ctx->l2; p.ln = ctx->ln; p.consts = ctx->d_consts; p.n2_0inv = ctx->n2_0inv; p.n_0inv = ctx->n_0inv;
@@ -1089,6 +1109,29 @@ int dkg_combine_ctx_create(int device, const uint32_t* n, int n_limbs, const uin
   cudaError_t e = cudaMalloc(&ctx->d_consts, consts.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { dkg_combine_ctx_destroy(ctx); return fail(DKG_ERR_CUDA, std::string("combine ctx: ") + cudaGetErrorString(e)); }
+  // warp-per-ciphertext kernel: R = 2^(32 Lc) >= 4 N^2
+  {
+    const int n2bits = dkg_host::bit_length(n2.data(), l2);
+    int cK = 0, cnb = 0;
+    if (env_long("DKG_COOP_COMBINE", 1) != 0 && coop_shape((n2bits + 2 + 31) / 32, &cK, &cnb)) {
+      const int Lc = cK * cnb;
+      dkg_host::Limbs N2c(Lc, 0), Nc(Lc, 0), thc(Lc, 0);
+      for (int i = 0; i < l2; ++i) N2c[i] = n2[i];
+      for (int i = 0; i < ln; ++i) { Nc[i] = nn[i]; thc[i] = th[i]; }
+      dkg_host::Limbs ni2 = dkg_host::neg_inv_block(N2c, Lc), nin = dkg_host::neg_inv_block(Nc, Lc);
+      dkg_host::Limbs rpow_c = dkg_host::pow2_mod((size_t)32 * Lc * shares, N2c);
+      dkg_host::Limbs thr_c = dkg_host::mulmod_slow(thc, dkg_host::pow2_mod((size_t)32 * Lc, Nc), Nc);
+      std::vector<uint32_t> cc;
+      for (const dkg_host::Limbs* v : {&N2c, &ni2, &rpow_c, &Nc, &nin, &thr_c}) cc.insert(cc.end(), v->begin(), v->end());
+      cudaError_t e2 = cudaMalloc(&ctx->d_cconsts, cc.size() * 4);
+      if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->d_cconsts, cc.data(), cc.size() * 4, cudaMemcpyHostToDevice);
+      if (e2 != cudaSuccess) { dkg_combine_ctx_destroy(ctx); return fail(DKG_ERR_CUDA, std::string("combine ctx (cooperative constants): ") + cudaGetErrorString(e2)); }
+      ctx->cK = cK; ctx->cnb = cnb;
+      ctx->cfull = make_coop_plan(cnb, 2 * cnb - 1);
+      ctx->clow = make_coop_plan(cnb, cnb);
+      ctx->coop = true;
+    }
+  }
   *out = ctx;
   return DKG_OK;
 }
@@ -1097,6 +1140,7 @@ void dkg_combine_ctx_destroy(dkg_combine_ctx* ctx) {
   if (!ctx) return;
   if (ctx->dev) cudaSetDevice(ctx->dev->device);
   if (ctx->d_consts) cudaFree(ctx->d_consts);
+  if (ctx->d_cconsts) cudaFree(ctx->d_cconsts);
   delete ctx;
 }
 

@@ -252,3 +252,57 @@ def test_constant_time_table_access_mode(native, coop):
                 ctx.close()
     finally:
         native.config_set("ct_table", 0)
+
+
+def test_cooperative_combine_equals_word_serial_kernel_and_python(native, monkeypatch):
+    """Share combination (paillier_shared_key.py:108-125): the warp-per-ciphertext kernel against the
+    thread-per-ciphertext one (DKG_COOP_COMBINE=0) and against Python integers, including the edge
+    values of the divisibility check: product 0, product 1 (message 0), tampered partials."""
+    from protocols.distributed_keygen_b200 import CombineContext
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+
+    rng = random.Random(5)
+    for bits, shares in ((67, 3), (515, 3), (2051, 5), (2048, 2), (3000, 3)):
+        p = rng.getrandbits(bits // 2) | 1 | (1 << (bits // 2 - 1))
+        q = rng.getrandbits(bits - bits // 2) | 1 | (1 << (bits - bits // 2 - 1))
+        n = p * q
+        n2 = n * n
+        theta_inv = rng.randrange(1, n)
+        count = 40
+        cols = []
+        for i in range(count):
+            parts = [rng.randrange(1, n2) for _ in range(shares - 1)]
+            prod = 1
+            for v in parts:
+                prod = prod * v % n2
+            # last partial chosen so that the product is 1 + m N (divisible), except every 5th
+            m = rng.randrange(n)
+            target = (1 + m * n) % n2 if i % 5 else rng.randrange(n2)
+            if i == 7:
+                target = 1          # message 0: y = 0
+            try:
+                last = target * pow(prod, -1, n2) % n2
+            except ValueError:
+                last = rng.randrange(n2)
+            if i == 9:
+                last = 0            # product 0
+            cols.append(parts + [last])
+        arr = np.stack([ints_to_limbs([cols[i][s] for i in range(count)], (n2.bit_length() + 31) // 32) for s in range(shares)])
+        want_val, want_st = [], []
+        for i in range(count):
+            x = 1
+            for v in cols[i]:
+                x = x * v % n2
+            ok = (x - 1) % n == 0
+            want_st.append(0 if ok else 2)
+            want_val.append(((x - 1) // n * theta_inv) % n if ok else 0)
+        outs = []
+        for coop in ("1", "0"):
+            monkeypatch.setenv("DKG_COOP_COMBINE", coop)
+            ctx = CombineContext(n, theta_inv, shares)
+            out, st = ctx.combine_limbs(arr)
+            ctx.close()
+            assert list(st) == want_st, (bits, coop)
+            assert limbs_to_ints(out) == want_val, (bits, coop)
+            outs.append(out)
+        assert np.array_equal(outs[0], outs[1])
