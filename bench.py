@@ -735,7 +735,7 @@ def main() -> None:
             py_secs = time.perf_counter() - t0
             assert got_int[:8] == limbs_to_ints(plain_host[:8])
             e2e["python_int_api"] = {"value": k_int / py_secs, "unit": UNIT, "batch": k_int,
-                                     "call": "distributed_keygen.decrypt_sequence_local (Python ints in and out, per-party calls)"}
+                                     "call": "distributed_keygen.decrypt_sequence_local (Python ints in, Python ints out, one engine call)"}
 
     # ---- true encryptions through the same kernels: decrypt(encrypt(m)) == m -------------------
     import random

@@ -1742,6 +1742,12 @@ int dkg_threshold_ctx_create(const int* devices, int ndev, const uint32_t* n, in
   }
   t->n_limbs = t->devs[0].combine->ln;
   t->l2 = t->devs[0].combine->l2;
+  if (env_long("DKG_CHUNK_ROWS", 0) <= 0) {
+    // chunks of whole kernel waves (4 of them): no partially filled last wave inside a shard
+    const dkg_modexp_ctx* c = t->devs[0].parties[0];
+    const size_t wave = (size_t)c->ctas * (size_t)(c->nsq ? c->nwarps : c->warps) * 32;
+    t->chunk_rows = std::max<size_t>(4 * wave, 1 << 16);
+  }
   *out = t;
   return DKG_OK;
 }

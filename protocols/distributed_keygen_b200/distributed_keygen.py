@@ -148,17 +148,42 @@ def decrypt_sequence_limbs(
     return plain
 
 
+_THRESHOLD_CACHE: dict[tuple, object] = {}
+
+
+def _cached_threshold_context(keys: Mapping[int, PaillierSharedKey], devices: Sequence[int] | None):
+    any_key = next(iter(keys.values()))
+    need = range(1, any_key.share.degree + 2)
+    ident = (any_key.n, tuple(keys[i].partial_decrypt_exponent() for i in need), tuple(devices) if devices is not None else None)
+    ctx = _THRESHOLD_CACHE.get(ident)
+    if ctx is None:
+        if len(_THRESHOLD_CACHE) >= 8:   # a handful of keys per process; drop the oldest
+            _THRESHOLD_CACHE.pop(next(iter(_THRESHOLD_CACHE))).close()
+        ctx = _THRESHOLD_CACHE[ident] = threshold_context(keys, devices)
+    return ctx
+
+
 def decrypt_sequence_local(
-    keys: Mapping[int, PaillierSharedKey], ciphertexts: Sequence[object], combiner: int | None = None
+    keys: Mapping[int, PaillierSharedKey], ciphertexts: Sequence[object], combiner: int | None = None,
+    devices: Sequence[int] | None = (0,),
 ) -> list[int]:
     """The arithmetic of ``_decrypt_sequence_raw`` (``:430-517``) when every party's key is in this
-    process: loop 1 (``:463-466``) = one batched partial decryption per party, loop 2
-    (``:510-515``) = one batched combination.  Returns the raw plaintext integers (what the
-    reference wraps in ``EncodedPlaintext``)."""
-    partials = {pid: key.partial_decrypt_batch(ciphertexts) for pid, key in keys.items()}
-    dicts = [{pid: partials[pid][i] for pid in keys} for i in range(len(ciphertexts))]
-    key = keys[combiner if combiner is not None else min(keys)]
-    return key.decrypt_batch(dicts)
+    process: loop 1 (``:463-466``, every party) and loop 2 (``:510-515``) in ONE engine call (the
+    ciphertexts are converted to limbs and uploaded once, the partials stay on the device).
+    Returns the raw plaintext integers (what the reference wraps in ``EncodedPlaintext``); raises
+    like the reference's per-element calls (``ZeroDivisionError`` / ``ValueError``)."""
+    any_key = keys[combiner if combiner is not None else min(keys)]
+    values = [any_key._raw_value(c) % any_key.n_square for c in ciphertexts]
+    ctx = _cached_threshold_context(keys, devices)
+    plain, status, _ = ctx.decrypt_limbs(ints_to_limbs(values, ctx.n2_limbs))
+    if (status == 1).any():
+        raise ZeroDivisionError("ciphertext not invertible modulo N^2")
+    if status.any():
+        raise ValueError(
+            "Combined decryption minus one is not divisible by N. This might be caused by the "
+            "fact that the ciphertext that is being decrypted, differs between the parties."
+        )
+    return limbs_to_ints(plain)
 
 
 def partial_decryption_message(key: PaillierSharedKey, ciphertext_rows: np.ndarray) -> bytes:

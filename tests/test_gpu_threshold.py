@@ -54,7 +54,6 @@ def test_threshold_context_matches_reference_vectors(fixture_vectors, dealer_vec
         keys = _gpu_keys(okeys_by_pid)
         good = [v for v in vectors if "error" not in v]
         n = keys[1].n
-        l2 = (2 * n.bit_length() + 31) // 32 if (n * n).bit_length() > 32 * ((2 * n.bit_length() + 31) // 32 - 1) else ((n * n).bit_length() + 31) // 32
         l2 = ((n * n).bit_length() + 31) // 32
         rows = ints_to_limbs([_h(v["c"]) for v in good], l2)
         for devices in _devices():
