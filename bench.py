@@ -91,6 +91,15 @@ def hbm_side(traffic_bytes: float, launch_ms: float) -> dict:
     return {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": src}
 
 
+# DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) of one launch of the shared-chain
+# kernel on 113 664 ciphertexts x 3 parties, from the committed capture (profiles/); None until captured
+MULTI_TRAFFIC_113664 = None
+
+
+def multi_traffic(B: int):
+    return None if MULTI_TRAFFIC_113664 is None else MULTI_TRAFFIC_113664 * B / 113664.0
+
+
 def canonical_modexp_macs(exp_bits: int, limbs: int) -> float:
     """modmul(L) = 2L^2 + L wide-MACs; modexp(E, L) = (E + ceil(E/5) + 32)
     modmuls (squarings counted as multiplies, canonical window 5)."""
@@ -119,6 +128,34 @@ def actual_modexp_macs(info: dict) -> float:
         sqr = (M * (M + 1) // 2 + M * M) * blk + M * lo
         mul = 2 * M * M * blk + M * lo
     return float(n_sqr * sqr + n_mul * mul)
+
+
+def pair_op_macs(K: int, M: int) -> tuple[float, float]:
+    """Wide multiply-accumulates of one squaring / one multiplication in the pair arithmetic modulo N
+    with M blocks of K limbs (csrc/dkg_nsq.cuh): (SQR(a) + doubled product, ad+bc + ac)."""
+    blk, lo = K * K, K * (K + 1) // 2
+    sqr = (M * (M + 1) // 2 + M * M) * blk + M * lo + 2 * M * M * blk + M * lo
+    mul = 3 * M * M * blk + M * lo + 2 * M * M * blk + M * lo
+    return float(sqr), float(mul)
+
+
+def shared_chain_macs(info_ex: list, shares: int) -> float:
+    """Wide multiply-accumulates the shared-squaring-chain kernel executes per CIPHERTEXT (all
+    `shares` partial decryptions): w (nwin - 1) squarings, and per party nwin bucket multiplications
+    + 2 (2^w - 2) for folding the buckets + 1 to leave the Montgomery domain; 1 to enter it."""
+    _, w, nwin, K, M = info_ex[:5]
+    sqr, mul = pair_op_macs(K, M)
+    return w * (nwin - 1) * sqr + (1 + shares * (nwin + 2 * ((1 << w) - 2) + 1)) * mul
+
+
+def threshold_info_ex(tctx) -> list:
+    import ctypes
+
+    from protocols.distributed_keygen_b200 import _native
+
+    arr = (ctypes.c_int * 8)()
+    _native.check(_native.lib.dkg_threshold_info_ex(tctx._h, ctypes.byref(arr)))
+    return list(arr)
 
 
 def random_units(count: int, n_square: int, limbs: int, seed: int):
@@ -398,9 +435,42 @@ def secondary_block(peak_tmacs: float) -> list:
     comb_macs = (4 * (2 * 128 * 128 + 128) + 2 * 64 * 64 + 64) * 1.0
     out.append({"config": "cfg3 combine-only, 5 partials (device-resident)", "count": Bc, "ms": round(cms, 3),
                 "per_s": round(Bc / cms * 1e3, 1), "canonical_frac": round(Bc * comb_macs / (cms * 1e-3) / 1e12 / peak_tmacs, 3)})
-    step_ms = sum(p["ms"] for p in per) + cms * per[0]["count"] / Bc
-    out.append({"config": "cfg3 threshold decrypt (5 partial decryptions + combination, sum of the launches above)",
-                "count": per[0]["count"], "ms": round(step_ms, 2), "per_s": round(per[0]["count"] / step_ms * 1e3, 1)})
+    # full threshold decryption of cfg3 through the one device-resident call (5 partial decryptions
+    # on one shared squaring chain + inversion of the negative parties' results + combination)
+    from protocols.distributed_keygen_b200 import _native
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkgmod
+
+    t3 = dkgmod.threshold_context(k3, [0])
+    ix3 = threshold_info_ex(t3)
+    B3 = per[0]["count"]
+    host3 = random_units(B3, c3.n * c3.n, t3.n2_limbs, 9)
+    d_c3 = torch.from_numpy(host3.view(np.int32)).cuda()
+    d_p3 = torch.empty((t3.shares, B3, t3.n2_limbs), dtype=torch.int32, device="cuda")
+    d_m3 = torch.empty((B3, t3.n_limbs), dtype=torch.int32, device="cuda")
+    d_s3 = torch.empty((t3.shares + 1) * B3, dtype=torch.uint8, device="cuda")
+
+    def call3():
+        _native.check(_native.lib.dkg_threshold_decrypt_batch_device(t3._h, d_c3.data_ptr(), d_m3.data_ptr(), d_p3.data_ptr(), d_s3.data_ptr(), B3, stream))
+
+    call3()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call3()
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms = e0.elapsed_time(e1)
+    got3 = d_p3[:, B3 - 1].cpu().numpy().view(np.uint32)
+    base3 = limbs_to_ints(host3[B3 - 1 :])[0]
+    for pi, pid in enumerate(sorted(ex3)):
+        assert limbs_to_ints(got3[pi : pi + 1])[0] == pow(base3, ex3[pid], c3.n * c3.n), "cfg3 shared chain"
+    t3.close()
+    ebits3 = max(abs(e).bit_length() for e in ex3.values())
+    out.append({"config": "cfg3 threshold decrypt, one device-resident call (5 partial decryptions%s + combination)"
+                          % (" on one shared squaring chain, w=%d" % ix3[1] if ix3[0] else ""),
+                "count": B3, "ms": round(step_ms, 2), "per_s": round(B3 / step_ms * 1e3, 1),
+                "canonical_frac": round(B3 * 5 * canonical_modexp_macs(ebits3, 128) / (step_ms * 1e-3) / 1e12 / peak_tmacs, 3),
+                "executed_frac": round(B3 * shared_chain_macs(ix3, 5) / (step_ms * 1e-3) / 1e12 / peak_tmacs, 3) if ix3[0] else None})
     for k in list(kreal.values()) + list(k3.values()):
         k.close()
     # cfg4: key_length 4096; encryption randomness at 2048 and 4096
@@ -620,23 +690,22 @@ def main() -> None:
     pinned_cts = torch.from_numpy(host_cts.view(np.int32)).pin_memory()
     d_cts = pinned_cts.cuda(non_blocking=True)
     d_partials = torch.empty((shares, B, L2), dtype=torch.int32, device="cuda")
-    d_pstatus = torch.empty((shares, B), dtype=torch.uint8, device="cuda")
     d_plain = torch.empty((B, Ln), dtype=torch.int32, device="cuda")
-    d_cstatus = torch.empty(B, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
-    modexp_events = []
+    # One step = the public device-resident call: all d+1 partial decryptions (ONE squaring chain
+    # shared by the parties, csrc/dkg_nsq.cuh modexp_nsq_multi_kernel; DKG_SHARED_SQUARINGS=0: one
+    # exponentiation per party) + inversion of the negative party's results + the combination.
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkgmod
+
+    dev_ctx = dkgmod.threshold_context(keys, [local_rank])
+    info_ex = threshold_info_ex(dev_ctx)
+    d_status = torch.empty((shares + 1) * B, dtype=torch.uint8, device="cuda")
+    d_pstatus, d_cstatus = d_status[: shares * B].view(shares, B), d_status[shares * B :]
 
     def device_step(record: bool) -> None:
-        for s, pid in enumerate(range(1, shares + 1)):
-            if record:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            ctxs[pid].modexp_device(d_cts.data_ptr(), d_partials[s].data_ptr(), d_pstatus[s].data_ptr(), B, stream)
-            if record:
-                e1.record()
-                modexp_events.append((pid, e0, e1))
-        comb.combine_device(d_partials.data_ptr(), d_plain.data_ptr(), d_cstatus.data_ptr(), B, stream)
+        _native.check(_native.lib.dkg_threshold_decrypt_batch_device(
+            dev_ctx._h, d_cts.data_ptr(), d_plain.data_ptr(), d_partials.data_ptr(), d_status.data_ptr(), B, stream))
 
     # ---- roofline denominator: measured on this GPU, now -------------------------------------
     import ctypes
@@ -646,6 +715,9 @@ def main() -> None:
 
     for _ in range(args.warmup):
         device_step(False)
+    torch.cuda.synchronize()
+    _native.config_set("time_kernels", 1)   # CUDA events around every launch of the exponentiation kernel, on its stream
+    _native.kernel_times(local_rank)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -658,6 +730,8 @@ def main() -> None:
     ev1.record()
     barrier()
     launches = eng.launch_count() - launches0
+    kernel_ms = _native.kernel_times(local_rank)
+    _native.config_set("time_kernels", 0)
     clocks = sampler.stop() if rank == 0 else {}
     elapsed_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
@@ -693,7 +767,7 @@ def main() -> None:
     if not args.no_e2e:
         from protocols.distributed_keygen_b200 import distributed_keygen as dkgmod
 
-        tctx = dkgmod.threshold_context(keys, [local_rank])
+        tctx = dev_ctx
         pinned_partials = torch.empty((shares, B, L2), dtype=torch.int32).pin_memory()
         pinned_plain = torch.empty((B, Ln), dtype=torch.int32).pin_memory()
         pinned_status = torch.empty(B, dtype=torch.uint8).pin_memory()
@@ -751,13 +825,18 @@ def main() -> None:
     assert got == ms, "threshold decryption round trip failed"
 
     if rank == 0:
-        # dominant kernel: modexp_fixed_kernel; per-launch duration from its own events
-        durs = [e0.elapsed_time(e1) for (_, e0, e1) in modexp_events]
-        avg_ms = sum(durs) / len(durs)
+        # dominant kernel: its launches were bracketed by CUDA events on their stream inside the timed
+        # region (dkg_kernel_times).  Shared chain: ONE launch per step does all `shares`
+        # exponentiations of the batch; otherwise one launch per party.
+        shared_chain = bool(info_ex[0])
+        avg_ms = sum(kernel_ms) / len(kernel_ms)
+        assert len(kernel_ms) == args.steps * (1 if shared_chain else shares), "kernel launch count"
+        modexps_per_launch = shares if shared_chain else 1
         ebits = sum(abs(exps[pid]).bit_length() for pid in exps) / len(exps)
-        macs_per_launch = B * canonical_modexp_macs(int(round(ebits)), L2)
+        macs_per_launch = B * modexps_per_launch * canonical_modexp_macs(int(round(ebits)), L2)
         achieved = macs_per_launch / (avg_ms * 1e-3) / 1e12
-        actual = B * actual_modexp_macs(info) / (avg_ms * 1e-3) / 1e12
+        actual = B * (shared_chain_macs(info_ex, shares) if shared_chain else actual_modexp_macs(info)) / (avg_ms * 1e-3) / 1e12
+        kname = ("modexp_nsq_multi_kernel<%d,%d>" if shared_chain else "modexp_nsq_kernel<%d,%d>") % (info["pair_K"], info["pair_M"])
         # roofline denominator: the better of the two register-resident IMAD.WIDE probes measured
         # in this run (ptxas issues every IMAD.WIDE at 4-cycle intervals per sub-partition, so both
         # forms top out near 32 wide-MAC/clk/SM = 9.3 T/s at 1965 MHz)
@@ -782,20 +861,24 @@ def main() -> None:
                 # captured once on a 113 664-ciphertext launch (profiles/r01_ncu_nsq_traffic_final.csv:
                 # 37.80 GB + 8.72 GB, window tables spilling out of L2), scaled to this launch's size;
                 # only known for the pair-arithmetic kernel at 2048-bit N
-                "traffic": (46.523e9 * B / 113664.0) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None,
+                "traffic": multi_traffic(B) if shared_chain else ((46.523e9 * B / 113664.0) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None),
                 "traffic_unit": "bytes per launch (DRAM, from the committed ncu capture)",
                 # the HBM side of the roofline, to show the kernel is nowhere near it
-                "hbm": hbm_side(46.523e9 * B / 113664.0, avg_ms) if (info.get("pair_arithmetic") and info.get("pair_K") == 14) else None,
-                "kernel": ("modexp_nsq_kernel<%d,%d>" % (info["pair_K"], info["pair_M"])) if info.get("pair_arithmetic")
-                else ("modexp_fixed_kernel<%d,%d>" % (info["K"], info["M"])),
+                "hbm": (hbm_side(multi_traffic(B), avg_ms) if (shared_chain and multi_traffic(B)) else
+                        hbm_side(46.523e9 * B / 113664.0, avg_ms) if (not shared_chain and info.get("pair_arithmetic") and info.get("pair_K") == 14) else None),
+                "kernel": kname, "kernel_share_of_step": avg_ms * len(kernel_ms) / max_ms,
+                "modexps_per_launch": B * modexps_per_launch,
+                "shared_squaring_chain": ({"window_bits": info_ex[1], "windows": info_ex[2]} if shared_chain else None),
                 "actual_wide_mac": actual, "frac_actual": actual / peak,
                 "avg_launch_ms": avg_ms, "algorithmic_macs_per_launch": macs_per_launch,
                 "peak_source": "dkg_measure_imad_peak, measured in this run: max of register-resident mad.wide.u32 (plain) and mad.lo.cc/madc.hi.cc (carry chain) probes",
                 "peak_plain_mad_wide": plain.value / 1e12,
                 "peak_carry_chain": carry.value / 1e12,
-                "note": "achieved = canonical work of SURVEY 8(d) (2L^2+L per modmul at L=limbs of N^2, squarings as multiplies); "
-                        "the kernel computes the same results with fewer multiplies (block squaring; for N^2 moduli pair arithmetic "
-                        "modulo N, csrc/dkg_nsq.cuh), so achieved/peak can exceed 1; frac_actual = multiplies really executed / peak",
+                "note": "achieved = canonical work of SURVEY 8(d) (2L^2+L per modmul at L=limbs of N^2, squarings as multiplies, one "
+                        "independent exponentiation per partial decryption) / the kernel's measured duration; the kernel computes the same "
+                        "partial decryptions with fewer multiplies (block squaring; pair arithmetic modulo N; ONE squaring chain shared by "
+                        "the parties of a ciphertext, csrc/dkg_nsq.cuh), so achieved/peak exceeds 1; frac_actual = multiplies really "
+                        "executed / peak is the pipe-level figure",
             },
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -81,6 +81,11 @@ unsigned long long dkg_launch_count(void);
  *                      DKG_COOP_GROUPED_MAX. */
 int dkg_config_set(const char* key, long value);
 int dkg_config_get(const char* key, long* value);
+/* With dkg_config_set("time_kernels", 1) every launch of an exponentiation kernel of the pair
+ * arithmetic (modexp_nsq_kernel, modexp_nsq_multi_kernel) is bracketed by CUDA events on its
+ * stream; this call waits for the recorded launches of `device`, returns their durations
+ * (milliseconds, in launch order, at most `capacity`) and forgets them. */
+int dkg_kernel_times(int device, double* ms, int capacity, int* count);
 
 /* Register-resident mad.wide.u32 microbenchmark: wide multiply-accumulates per second of the
  * integer multiplier on `device`, plain (no carry) and carry-chained.  The roofline denominator. */
@@ -146,11 +151,24 @@ int dkg_threshold_ctx_create(const int* devices, int ndev, const uint32_t* n, in
 void dkg_threshold_ctx_destroy(dkg_threshold_ctx* ctx);
 /* info[0]=devices, [1]=shares, [2]=limbs of N, [3]=limbs of N^2 */
 int dkg_threshold_info(const dkg_threshold_ctx* ctx, int info[4]);
+/* info[0]=1 if the parties share one squaring chain (see below), [1]=its window bits, [2]=its windows,
+ * [3],[4]=block size / block count of the pair kernel, [5]=warps per CTA, [6]=CTAs, [7]=rows per chunk */
+int dkg_threshold_info_ex(const dkg_threshold_ctx* ctx, int info[8]);
 /* ciphertexts [count][n2_limbs] -> plaintexts [count][n_limbs]; the ciphertexts are uploaded once,
  * the partial decryptions stay on the device unless `partials` ([shares][count][n2_limbs]) is given.
  * status[count] (or NULL): the first party's non-zero modexp status, else the combination's. */
 int dkg_threshold_decrypt_batch(dkg_threshold_ctx* ctx, const uint32_t* ciphertexts,
                                 uint32_t* plaintexts, uint32_t* partials, uint8_t* status, size_t count);
+/* The same with everything resident on the context's first device, enqueued on `stream` (a
+ * cudaStream_t), no copies: d_partials [shares][count][n2_limbs] and d_status [(shares+1)][count]
+ * (every party's modexp status, then the combination's) are required work areas / outputs.
+ * With two or more parties whose keys use the pair arithmetic, the d+1 exponentiations of a batch
+ * share ONE chain of squarings (right-to-left bucket method, csrc/dkg_nsq.cuh): every partial
+ * decryption is still produced, bit-identical to the party's own call.  DKG_SHARED_SQUARINGS=0
+ * turns that off (one left-to-right exponentiation per party). */
+int dkg_threshold_decrypt_batch_device(dkg_threshold_ctx* ctx, const uint32_t* d_ciphertexts,
+                                       uint32_t* d_plaintexts, uint32_t* d_partials,
+                                       uint8_t* d_status, size_t count, void* stream);
 /* one party's partial decryptions (what a distributed party computes for its broadcast) */
 int dkg_threshold_partial_decrypt_batch(dkg_threshold_ctx* ctx, int party, const uint32_t* ciphertexts,
                                         uint32_t* out, uint8_t* status, size_t count);

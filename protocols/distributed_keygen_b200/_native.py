@@ -28,12 +28,13 @@ STATUS_OUT_OF_RANGE = 3
 # every symbol include/dkg_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "dkg_version", "dkg_last_error", "dkg_device_count", "dkg_launch_count",
-    "dkg_measure_imad_peak", "dkg_config_set", "dkg_config_get",
+    "dkg_measure_imad_peak", "dkg_config_set", "dkg_config_get", "dkg_kernel_times",
     "dkg_modexp_ctx_create", "dkg_modexp_ctx_create_nsq", "dkg_modexp_ctx_destroy", "dkg_modexp_ctx_info",
     "dkg_modexp_batch", "dkg_modexp_batch_device",
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
     "dkg_combine_batch", "dkg_combine_batch_device",
-    "dkg_threshold_ctx_create", "dkg_threshold_ctx_destroy", "dkg_threshold_info", "dkg_threshold_decrypt_batch",
+    "dkg_threshold_ctx_create", "dkg_threshold_ctx_destroy", "dkg_threshold_info", "dkg_threshold_info_ex", "dkg_threshold_decrypt_batch",
+    "dkg_threshold_decrypt_batch_device",
     "dkg_threshold_partial_decrypt_batch", "dkg_threshold_combine_batch", "dkg_host_register", "dkg_host_unregister",
     "dkg_encrypt_batch", "dkg_modexp_grouped",
     "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve", "dkg_biprime_verdict",
@@ -81,6 +82,9 @@ def _load() -> ctypes.CDLL:
     lib.dkg_threshold_ctx_destroy.restype = None
     lib.dkg_threshold_info.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 4)]
     lib.dkg_threshold_decrypt_batch.argtypes = [c_void, c_u32p, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
+    lib.dkg_kernel_times.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double * 4096), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.dkg_threshold_info_ex.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 8)]
+    lib.dkg_threshold_decrypt_batch_device.argtypes = [c_void, c_void, c_void, c_void, c_void, ctypes.c_size_t, c_void]
     lib.dkg_threshold_partial_decrypt_batch.argtypes = [c_void, ctypes.c_int, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_threshold_combine_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_host_register.argtypes = [c_void, ctypes.c_size_t]
@@ -115,6 +119,16 @@ def config_get(key: str) -> int:
     v = ctypes.c_long(0)
     check(lib.dkg_config_get(key.encode(), ctypes.byref(v)))
     return int(v.value)
+
+
+def kernel_times(device: int = 0, capacity: int = 4096) -> list[float]:
+    """Durations (ms) of the exponentiation-kernel launches recorded since the last call
+    (``config_set("time_kernels", 1)`` turns the recording on)."""
+    capacity = 4096
+    buf = (ctypes.c_double * capacity)()
+    n = ctypes.c_int(0)
+    check(lib.dkg_kernel_times(device, buf, capacity, ctypes.byref(n)))
+    return [float(buf[i]) for i in range(n.value)]
 
 
 def device_count() -> int:

@@ -71,6 +71,9 @@ BatchInvFn lookup_batchinv_group4(int, int); BatchInvFn lookup_batchinv_group5(i
 using NsqFn = void (*)(const NsqParams);
 NsqFn lookup_nsq_group0(int, int); NsqFn lookup_nsq_group1(int, int); NsqFn lookup_nsq_group2(int, int);
 NsqFn lookup_nsq_group3(int, int); NsqFn lookup_nsq_group4(int, int); NsqFn lookup_nsq_group5(int, int);
+using NsqMultiFn = void (*)(const NsqMultiParams);
+NsqMultiFn lookup_nsq_multi_group0(int, int); NsqMultiFn lookup_nsq_multi_group1(int, int); NsqMultiFn lookup_nsq_multi_group2(int, int);
+NsqMultiFn lookup_nsq_multi_group3(int, int); NsqMultiFn lookup_nsq_multi_group4(int, int); NsqMultiFn lookup_nsq_multi_group5(int, int);
 using GroupedFn = void (*)(const GroupedParams);
 GroupedFn lookup_grouped_group0(int, int); GroupedFn lookup_grouped_group1(int, int);
 GroupedFn lookup_grouped_group2(int, int); GroupedFn lookup_grouped_group3(int, int);
@@ -120,6 +123,19 @@ struct DeviceState {
   size_t aux_words = 0;
   cudaEvent_t last = nullptr;  // end of the latest launch sequence that used scratch / aux / counter
   std::mutex mu;            // held while a launch sequence is enqueued (and, for host buffers, until it is done)
+  // event pairs around the exponentiation kernels' launches (config "time_kernels"), read and
+  // cleared by dkg_kernel_times: the kernel's own duration for the roofline, measured in place
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktimes;
+};
+std::atomic<long> g_time_kernels{0};
+struct KernelTimer {
+  DeviceState* d; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(DeviceState* d_, cudaStream_t s_) : d(d_), s(s_) {
+    if (g_time_kernels.load() == 0 || d->ktimes.size() >= 4096) return;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+    cudaEventRecord(e0, s);
+  }
+  ~KernelTimer() { if (e1) { cudaEventRecord(e1, s); d->ktimes.emplace_back(e0, e1); } }
 };
 
 // All contexts of a device share its scratch areas and the work ticket.  Every launch sequence --
@@ -619,7 +635,10 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   q.pairs_in = pairs; q.pairs_out = pairs; q.count = count; q.consts = ctx->d_nconsts; q.ops = ctx->d_ops;
   q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd; q.ct_table = ctx->ct_table ? 1 : 0; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
   q.scratch_q_offset = ctx->nscratch_q_offset; q.counter = d->counter;
-  ctx->nsq_kernel<<<ctas, ctx->nwarps * 32, ctx->nsmem, stream>>>(q);
+  {
+    KernelTimer kt(d, stream);
+    ctx->nsq_kernel<<<ctas, ctx->nwarps * 32, ctx->nsmem, stream>>>(q);
+  }
   dkg::NsqIoParams x = e;
   x.in = pairs; x.out = d_out; x.mrows = d_mrows; x.m_limbs = m_limbs;
   dkg::nsq_exit_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(x);
@@ -635,6 +654,14 @@ dkg::NsqFn lookup_nsq(int K, int M) {
                                       dkg::lookup_nsq_group3, dkg::lookup_nsq_group4, dkg::lookup_nsq_group5};
   for (auto g : groups)
     if (dkg::NsqFn f = g(K, M)) return f;
+  return nullptr;
+}
+
+dkg::NsqMultiFn lookup_nsq_multi(int K, int M) {
+  dkg::NsqMultiFn (*groups[])(int, int) = {dkg::lookup_nsq_multi_group0, dkg::lookup_nsq_multi_group1, dkg::lookup_nsq_multi_group2,
+                                           dkg::lookup_nsq_multi_group3, dkg::lookup_nsq_multi_group4, dkg::lookup_nsq_multi_group5};
+  for (auto g : groups)
+    if (dkg::NsqMultiFn f = g(K, M)) return f;
   return nullptr;
 }
 
@@ -669,6 +696,7 @@ int dkg_config_set(const char* key, long value) {
   if (k == "coop_max") { coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault); g_coop_max.store(value); return DKG_OK; }
   if (k == "coop_grouped_max") { g_coop_grouped_max.store(value); return DKG_OK; }
   if (k == "ct_table") { g_ct_table.store(value ? 1 : 0); return DKG_OK; }
+  if (k == "time_kernels") { g_time_kernels.store(value ? 1 : 0); return DKG_OK; }
   return fail(DKG_ERR_INVALID, "unknown configuration key");
 }
 int dkg_config_get(const char* key, long* value) {
@@ -677,7 +705,26 @@ int dkg_config_get(const char* key, long* value) {
   if (k == "coop_max") { *value = (long)coop_limit(g_coop_max, "DKG_COOP_MAX", kCoopMaxDefault); return DKG_OK; }
   if (k == "coop_grouped_max") { *value = (long)coop_limit(g_coop_grouped_max, "DKG_COOP_GROUPED_MAX", kCoopGroupedMaxDefault); return DKG_OK; }
   if (k == "ct_table") { *value = ct_table_setting() ? 1 : 0; return DKG_OK; }
+  if (k == "time_kernels") { *value = g_time_kernels.load(); return DKG_OK; }
   return fail(DKG_ERR_INVALID, "unknown configuration key");
+}
+
+int dkg_kernel_times(int device, double* ms, int capacity, int* count) {
+  if (!count || capacity < 0 || (capacity > 0 && !ms)) return fail(DKG_ERR_INVALID, "null argument");
+  DeviceState* d = nullptr;
+  int rc = device_state(device, &d);
+  if (rc != DKG_OK) return rc;
+  std::lock_guard<std::mutex> lk(d->mu);
+  CUDA_TRY(cudaSetDevice(d->device));
+  int n = 0;
+  for (auto& pr : d->ktimes) {
+    float t = 0.f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess && n < capacity) ms[n++] = (double)t;
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
+  d->ktimes.clear();
+  *count = n;
+  return DKG_OK;
 }
 
 int dkg_modexp_ctx_create(int device, const uint32_t* modulus, int mod_limbs, const uint32_t* exponent,
@@ -1567,6 +1614,11 @@ struct dkg_threshold_ctx {
     std::vector<dkg_modexp_ctx*> parties;
     dkg_combine_ctx* combine = nullptr;
     cudaStream_t streams[2] = {nullptr, nullptr};
+    // shared squaring chain (modexp_nsq_multi_kernel): right-to-left digits of every party
+    dkg::NsqMultiFn multi_kernel = nullptr;
+    uint8_t* d_digits = nullptr;     // [shares][multi_nwin]
+    int multi_w = 0, multi_nwin = 0;
+    size_t multi_scratch_per_warp = 0, multi_q_offset = 0;
   };
   int shares = 0, n_limbs = 0, l2 = 0;
   size_t chunk_rows = 1 << 18;
@@ -1580,6 +1632,88 @@ std::vector<Shard> shard_rows(size_t count, size_t parts) {
   std::vector<Shard> out(parts);
   for (size_t r = 0; r < parts; ++r) out[r] = Shard{count * r / parts, count * (r + 1) / parts};
   return out;
+}
+
+// All parties' exponentiations of `rows` ciphertexts through ONE squaring chain (dkg_nsq.cuh,
+// modexp_nsq_multi_kernel): entry -> multi kernel -> exit for every party; a party with a negative
+// exponent gets the batched inversion applied to its RESULTS, (c^-1)^|e| = (c^|e|)^-1 (same canonical
+// residue), and if a chain of that inversion met a non-unit the party's direct kernel redoes its
+// rows on the same stream, predicated on the device-side flag, with the exact per-element status.
+// d_part: [S][rows][l2], d_st: [S][rows].
+int launch_threshold_multi(dkg_threshold_ctx::Dev& dv, int S, const uint32_t* d_bases, uint32_t* d_part, uint8_t* d_st,
+                           size_t rows, cudaStream_t stream) {
+  dkg_modexp_ctx* c0 = dv.parties[0];
+  DeviceState* d = dv.dev;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const int Lp = c0->nLp, l2 = c0->limbs;
+  const unsigned long long ngroups = (rows + 31) / 32;
+  const size_t pair_words = rows * (size_t)(2 * Lp);
+  bool any_neg = false;
+  for (int p = 0; p < S; ++p) any_neg = any_neg || dv.parties[p]->negative;
+  const size_t gwords = (size_t)c0->Lp * 32;
+  const int nchain = inversion_chain_warps(d, c0, ngroups);
+  const int chain_len = (int)((ngroups + nchain - 1) / nchain);
+  const size_t inv_words = any_neg ? 2 * ngroups * gwords + (size_t)nchain * gwords + (size_t)nchain * 32 + 32 * (size_t)S : 0;
+  int rc = ensure_aux(d, (size_t)(S + 1) * pair_words + inv_words);
+  const int total_warps = c0->ctas * c0->nwarps;
+  size_t scratch_words = (size_t)total_warps * dv.multi_scratch_per_warp;
+  if (any_neg) scratch_words = std::max(scratch_words, (size_t)c0->ctas * c0->warps * c0->scratch_per_warp);
+  if (rc == DKG_OK) rc = ensure_scratch(d, scratch_words);
+  if (rc != DKG_OK) return rc;
+  uint32_t* pairs_in = d->aux;
+  uint32_t* pairs_out = d->aux + pair_words;
+  uint32_t* inv_area = pairs_out + (size_t)S * pair_words;
+  CUDA_TRY(cudaMemsetAsync(d_st, 0, rows * (size_t)S, stream));
+  dkg::NsqIoParams e{};
+  e.in = d_bases; e.out = pairs_in; e.count = rows; e.io_limbs = l2; e.Lp = Lp; e.consts = c0->d_nio; e.n0inv = c0->n_n0inv;
+  e.mrows = nullptr; e.m_limbs = 0;
+  dkg::nsq_entry_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, stream>>>(e);
+  CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
+  int ctas = c0->ctas;
+  if (ngroups < (unsigned long long)total_warps) ctas = (int)((ngroups + c0->nwarps - 1) / c0->nwarps);
+  dkg::NsqMultiParams q{};
+  q.pairs_in = pairs_in; q.pairs_out = pairs_out; q.count = rows; q.consts = c0->d_nconsts; q.digits = dv.d_digits;
+  q.nparties = S; q.nwin = dv.multi_nwin; q.wbits = dv.multi_w; q.scratch = d->scratch;
+  q.scratch_per_warp = dv.multi_scratch_per_warp; q.scratch_q_offset = dv.multi_q_offset; q.counter = d->counter;
+  {
+    KernelTimer kt(d, stream);
+    dv.multi_kernel<<<ctas, c0->nwarps * 32, c0->nsmem, stream>>>(q);
+  }
+  dkg::NsqIoParams x = e;
+  x.in = pairs_out; x.out = d_part; x.count = rows * (size_t)S;
+  dkg::nsq_exit_kernel<<<(unsigned)((x.count + 63) / 64), 64, 0, stream>>>(x);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(3);
+  for (int p = 0; p < S; ++p) {
+    dkg_modexp_ctx* c = dv.parties[p];
+    uint32_t* out_p = d_part + (size_t)p * rows * l2;
+    if (c->negative) {
+      dkg::BatchInvParams b{};
+      b.bases = out_p; b.count = rows; b.in_limbs = l2; b.consts = c->d_consts; b.n0inv = c->n0inv;
+      b.chain_s = inv_area; b.chain_p = inv_area + ngroups * gwords; b.scratch = inv_area + 2 * ngroups * gwords;
+      b.chain_status = b.scratch + (size_t)nchain * gwords;
+      b.any_bad = reinterpret_cast<unsigned int*>(b.chain_status + (size_t)nchain * 32 + 32 * (size_t)p);
+      b.plain_out = out_p;   // in place: a chain warp reads all its groups before it writes any
+      b.nchain_warps = nchain; b.chain_len = chain_len;
+      CUDA_TRY(cudaMemsetAsync(b.any_bad, 0, sizeof(unsigned int), stream));
+      const int blocks = (nchain + c->inv_warps - 1) / c->inv_warps;
+      c->inv_kernel<<<blocks, c->inv_warps * 32, c->inv_smem, stream>>>(b);
+      CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), stream));
+      dkg::ModexpParams m{};
+      m.bases = d_bases; m.out = out_p; m.status = d_st + (size_t)p * rows; m.count = rows; m.in_limbs = l2;
+      m.consts = c->d_consts; m.ops = c->d_ops; m.nops = c->nops; m.tab_entries = c->tab_entries; m.table_odd = c->table_odd;
+      m.negative = 1; m.n0inv = c->n0inv; m.scratch = d->scratch; m.scratch_per_warp = c->scratch_per_warp;
+      m.scratch_q_offset = c->scratch_q_offset; m.counter = d->counter; m.run_if = b.any_bad;
+      int dctas = c->ctas;
+      if (ngroups < (unsigned long long)(c->ctas * c->warps)) dctas = (int)((ngroups + c->warps - 1) / c->warps);
+      c->kernel<<<dctas, c->warps * 32, c->smem, stream>>>(m);
+      CUDA_TRY(cudaGetLastError());
+      g_launches.fetch_add(2);
+    }
+    rc = launch_range_check(c, d_bases, out_p, d_st + (size_t)p * rows, rows, stream);
+    if (rc != DKG_OK) return rc;
+  }
+  return DKG_OK;
 }
 
 // what one device does with its shard, chunk by chunk, alternating between its two streams so the
@@ -1658,7 +1792,9 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
           // (party, ciphertext)); otherwise one wave launch per party
           bool fused = S <= dkg::kCoopMaxParties;
           for (int p = 0; p < S; ++p) fused = fused && dv.parties[p]->coop && dv.parties[p]->use_nsq && rows * (size_t)S <= dv.parties[p]->coop_max;
-          if (fused) {
+          if (!fused && dv.multi_kernel != nullptr) {
+            rc = launch_threshold_multi(dv, S, B.in, B.part, B.st, rows, s);
+          } else if (fused) {
             rc = launch_modexp_coop_parties(dv.parties.data(), S, B.in, B.part, B.st, rows, s, nullptr, 0);
             for (int p = 0; p < S && rc == DKG_OK; ++p)
               rc = launch_range_check(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, rows, s);
@@ -1711,6 +1847,58 @@ int run_threshold(dkg_threshold_ctx* t, const ThresholdJob& job) {
   return DKG_OK;
 }
 
+// Shared squaring chain for a device's parties (launch_threshold_multi): eligible when there are at
+// least two of them, all on the pair arithmetic with one shape, table access not in constant-time
+// mode, and the batched inversion available if an exponent is negative.  Window width: fewest
+// multiplications per party, ceil(E / w) + 2 (2^w - 2), under a cap on the bucket scratch.
+int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t* exponents, int exp_limbs) {
+  if (shares < 2 || shares > dkg::kNsqMultiMaxParties || env_long("DKG_SHARED_SQUARINGS", 1) == 0) return DKG_OK;
+  const dkg_modexp_ctx* c0 = dv.parties[0];
+  int ebits = 1;
+  for (int p = 0; p < shares; ++p) {
+    const dkg_modexp_ctx* c = dv.parties[p];
+    if (!c->nsq || !c->use_nsq || c->ct_table || c->nshape.K != c0->nshape.K || c->nshape.M != c0->nshape.M) return DKG_OK;
+    if (c->negative && c->inv_kernel == nullptr) return DKG_OK;
+    ebits = std::max(ebits, c->ebits);
+  }
+  dkg::NsqMultiFn kernel = lookup_nsq_multi(c0->nshape.K, c0->nshape.M);
+  if (!kernel) return DKG_OK;
+  const size_t slot_words = (size_t)2 * c0->nLp * 32;   // one pair in lane layout
+  const size_t total_warps = (size_t)c0->ctas * c0->nwarps;
+  const size_t cap_words = (size_t)env_long("DKG_MULTI_SCRATCH_MB", 24576) * (1u << 18);
+  int best = 0;
+  long best_cost = -1;
+  for (int w = 1; w <= 8; ++w) {
+    const size_t words = total_warps * (((size_t)shares << w) + 2) * slot_words;
+    if (w > 1 && words > cap_words) break;
+    const long cost = (ebits + w - 1) / w + 2 * ((1L << w) - 2);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
+  }
+  if (long f = env_long("DKG_MULTI_WINDOW", 0); f >= 1 && f <= 8) best = (int)f;
+  const int w = best, nwin = (ebits + w - 1) / w;
+  std::vector<uint8_t> digits((size_t)shares * nwin, 0);
+  for (int p = 0; p < shares; ++p) {
+    const uint32_t* e = exponents + (size_t)p * exp_limbs;
+    for (int k = 0; k < nwin; ++k) {
+      unsigned dgt = 0;
+      for (int b = 0; b < w; ++b) {
+        const int bit = k * w + b;
+        if (bit < 32 * exp_limbs && ((e[bit / 32] >> (bit % 32)) & 1u)) dgt |= 1u << b;
+      }
+      digits[(size_t)p * nwin + k] = (uint8_t)dgt;
+    }
+  }
+  CUDA_TRY(cudaSetDevice(dv.dev->device));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c0->nsmem));
+  CUDA_TRY(cudaMalloc(&dv.d_digits, digits.size()));
+  CUDA_TRY(cudaMemcpy(dv.d_digits, digits.data(), digits.size(), cudaMemcpyHostToDevice));
+  dv.multi_w = w; dv.multi_nwin = nwin;
+  dv.multi_q_offset = (((size_t)shares << w) + 2) * slot_words;
+  dv.multi_scratch_per_warp = dv.multi_q_offset + (size_t)c0->nLp * 32;
+  dv.multi_kernel = kernel;
+  return DKG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1732,6 +1920,7 @@ int dkg_threshold_ctx_create(const int* devices, int ndev, const uint32_t* n, in
       if (rc == DKG_OK) dv.parties.push_back(c);
     }
     if (rc == DKG_OK) rc = dkg_combine_ctx_create(devices[i], n, n_limbs, theta_inv, shares, &dv.combine);
+    if (rc == DKG_OK) rc = setup_threshold_multi(dv, shares, exponents, exp_limbs);
     if (rc == DKG_OK) {
       cudaSetDevice(devices[i]);
       for (int b = 0; b < 2 && rc == DKG_OK; ++b)
@@ -1759,6 +1948,7 @@ void dkg_threshold_ctx_destroy(dkg_threshold_ctx* t) {
     for (auto* c : dv.parties) dkg_modexp_ctx_destroy(c);
     dkg_combine_ctx_destroy(dv.combine);
     for (auto s : dv.streams) if (s) cudaStreamDestroy(s);
+    if (dv.d_digits) cudaFree(dv.d_digits);
   }
   delete t;
 }
@@ -1769,12 +1959,48 @@ int dkg_threshold_info(const dkg_threshold_ctx* t, int info[4]) {
   return DKG_OK;
 }
 
+int dkg_threshold_info_ex(const dkg_threshold_ctx* t, int info[8]) {
+  if (!t || !info) return fail(DKG_ERR_INVALID, "null argument");
+  const dkg_threshold_ctx::Dev& dv = t->devs[0];
+  info[0] = dv.multi_kernel != nullptr ? 1 : 0; info[1] = dv.multi_w; info[2] = dv.multi_nwin;
+  info[3] = dv.parties[0]->nshape.K; info[4] = dv.parties[0]->nshape.M; info[5] = dv.parties[0]->nwarps;
+  info[6] = dv.parties[0]->ctas; info[7] = (int)std::min<size_t>(t->chunk_rows, 0x7fffffff);
+  return DKG_OK;
+}
+
 int dkg_threshold_decrypt_batch(dkg_threshold_ctx* t, const uint32_t* ciphertexts, uint32_t* plaintexts, uint32_t* partials,
                                 uint8_t* status, size_t count) {
   if (!t || (count && (!ciphertexts || !plaintexts))) return fail(DKG_ERR_INVALID, "null argument");
   ThresholdJob job;
   job.mode = 0; job.in = ciphertexts; job.plain = plaintexts; job.partials = partials; job.status = status; job.count = count;
   return run_threshold(t, job);
+}
+
+// Device-resident variant on the context's FIRST device: everything already in HBM, enqueued on the
+// caller's stream, no copies, no synchronisation.
+int dkg_threshold_decrypt_batch_device(dkg_threshold_ctx* t, const uint32_t* d_ciphertexts, uint32_t* d_plaintexts,
+                                       uint32_t* d_partials, uint8_t* d_status, size_t count, void* stream) {
+  if (!t || (count && (!d_ciphertexts || !d_plaintexts || !d_partials || !d_status))) return fail(DKG_ERR_INVALID, "null argument");
+  if (count == 0) return DKG_OK;
+  dkg_threshold_ctx::Dev& dv = t->devs[0];
+  cudaStream_t s = (cudaStream_t)stream;
+  const int S = t->shares;
+  DeviceLease lease(dv.dev, s);
+  bool fused = S <= dkg::kCoopMaxParties;
+  for (int p = 0; p < S; ++p) fused = fused && dv.parties[p]->coop && dv.parties[p]->use_nsq && count * (size_t)S <= dv.parties[p]->coop_max;
+  int rc = DKG_OK;
+  if (!fused && dv.multi_kernel != nullptr) {
+    rc = launch_threshold_multi(dv, S, d_ciphertexts, d_partials, d_status, count, s);
+  } else if (fused) {
+    rc = launch_modexp_coop_parties(dv.parties.data(), S, d_ciphertexts, d_partials, d_status, count, s, nullptr, 0);
+    for (int p = 0; p < S && rc == DKG_OK; ++p)
+      rc = launch_range_check(dv.parties[p], d_ciphertexts, d_partials + (size_t)p * count * t->l2, d_status + (size_t)p * count, count, s);
+  } else {
+    for (int p = 0; p < S && rc == DKG_OK; ++p)
+      rc = launch_modexp(dv.parties[p], d_ciphertexts, d_partials + (size_t)p * count * t->l2, d_status + (size_t)p * count, nullptr, count, s);
+  }
+  if (rc == DKG_OK) rc = launch_combine(dv.combine, d_partials, d_plaintexts, d_status + (size_t)S * count, count, s);
+  return rc;
 }
 
 int dkg_threshold_partial_decrypt_batch(dkg_threshold_ctx* t, int party, const uint32_t* ciphertexts, uint32_t* out,

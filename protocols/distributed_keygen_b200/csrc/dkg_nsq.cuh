@@ -248,4 +248,157 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   }
 }
 
+// ---- several exponents, one base: shared squaring chain ------------------------------------------
+// When the shares of several parties sit on one device (the reference's in-process parties,
+// distributed_keygen.py:203-226; the threshold context of this library), their partial decryptions
+// c^(e_1), ..., c^(e_P) of the SAME ciphertext need only ONE chain of squarings.  Right to left in
+// base D = 2^w:  c^(e_p) = prod_k (c^(D^k))^(digit_pk) = prod_{d=1}^{D-1} (A_pd)^d  with the buckets
+// A_pd = prod_{k: digit_pk = d} c^(D^k).  Per window: w squarings of the running power (shared by
+// all parties) and ONE multiplication per party into the bucket its digit names (digit 0 goes to a
+// dummy bucket: the operation sequence does not depend on the exponents).  The buckets are folded
+// with the running-product trick, T <- T * A_d, S <- S * T for d = D-2 .. 1: 2 (D - 2)
+// multiplications per party.  At 4190-bit exponents and w = 6: 4182 squarings + P * 822
+// multiplications instead of P * (4186 squarings + 724 multiplications): 2.05x fewer wide
+// multiply-accumulates for P = 3, 2.6x for P = 5.  Every party's result is the same canonical
+// residue as its own exponentiation would give (negative exponents: the caller inverts the RESULT,
+// (c^-1)^|e| = (c^|e|)^-1).
+//
+// The Montgomery product overwrites its shared-memory operand, so the running power is parked in
+// the warp's global scratch around every bucket multiplication (2 P + 1 copies of 2 Lp limbs per
+// window against 6 squarings + P multiplications: < 1 % of the instructions).
+template <int K, int M>
+__global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(const NsqMultiParams p) {
+  using V = typename VecSel<K>::T;
+  constexpr int VW = VecSel<K>::VW;
+  constexpr int Lp = K * M;
+  constexpr int LV = Lp / VW;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // same uniform area as modexp_nsq_kernel
+  constexpr int UNI0 = ((2 * Lp + K) * 4 + 15) / 16 * 16;
+  constexpr int UNI = UNI0 + (kNsqSchedWords<M> * 4 + 15) / 16 * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * Lp + K; i += blockDim.x) U32[i] = p.consts[i];
+  fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw + UNI0));
+  __syncthreads();
+  const uint32_t* Ns32 = U32;
+  const uint32_t* Dneg = U32 + Lp + K;
+
+  V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * 2 * LV * 32;
+  V* Bw = Aw + LV * 32;
+  uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
+  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
+  const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
+  const V* Crep = Cg + 6 * LV + lane;
+  const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
+          *ONEBr = Crep + (size_t)3 * LV * 32,
+          *PLAIN1r = Crep + (size_t)4 * LV * 32, *ZEROr = Crep + (size_t)5 * LV * 32;
+
+  const unsigned gwarp = blockIdx.x * nwarps + warp;
+  uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
+  V* slots = reinterpret_cast<V*>(scratch32);   // pair s: a at (2s)*LV*32, b right after
+  V* Qg = reinterpret_cast<V*>(scratch32 + p.scratch_q_offset);
+  const int D = 1 << p.wbits;
+  auto slot_a = [&](int s) -> V* { return slots + (size_t)s * 2 * LV * 32 + lane; };
+  auto slot_b = [&](int s) -> V* { return slots + ((size_t)s * 2 + 1) * LV * 32 + lane; };
+  const int CUR = p.nparties * D, ACC = CUR + 1;   // parked running power / bucket accumulator S
+
+  const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(Aw + lane);
+  const uint32_t b_s = (uint32_t)__cvta_generic_to_shared(Bw + lane);
+  WarpIO<K, M, false, true> io;
+  io.sched_s = (uint32_t)__cvta_generic_to_shared(smem_raw + UNI0);
+  io.ns = (uint32_t)__cvta_generic_to_shared(Ns32);
+  io.nis = (uint32_t)__cvta_generic_to_shared(Ns32 + Lp);
+  io.Qg = Qg + lane;
+
+  auto pair_mul = [&](const V* c, const V* d) {
+    io.xs = b_s; io.ss = a_s; io.Y = c; io.Y2 = d;
+    mont_call<K, M, MONT_MULADD, false, true>(io);
+    io.xs = a_s;
+    mont_call<K, M, MONT_MUL, false, true>(io);
+    pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
+  };
+  auto pair_sqr = [&]() {
+    io.xs = b_s; io.ss = a_s;
+    mont_call<K, M, MONT_MUL2S, false, true>(io);
+    io.xs = a_s;
+    mont_call<K, M, MONT_SQR, false, true>(io);
+    pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
+  };
+  auto park = [&](int s) {      // slot s <- (A, B)
+    V* da = slot_a(s); V* db = slot_b(s);
+#pragma unroll 5
+    for (int v = 0; v < LV; ++v) { da[(size_t)v * 32] = Aw[v * 32 + lane]; db[(size_t)v * 32] = Bw[v * 32 + lane]; }
+  };
+  auto fetch = [&](int s) {     // (A, B) <- slot s
+    const V* sa = slot_a(s); const V* sb = slot_b(s);
+#pragma unroll 5
+    for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = sa[(size_t)v * 32]; Bw[v * 32 + lane] = sb[(size_t)v * 32]; }
+  };
+
+  const unsigned long long ngroups = (p.count + 31ull) / 32ull;
+  for (;;) {
+    unsigned int g = 0;
+    if (lane == 0) g = atomicAdd(p.counter, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups) break;
+    const unsigned long long first = (unsigned long long)g * 32ull;
+    const int cnt = (int)((p.count - first) < 32ull ? (p.count - first) : 32ull);
+
+    for (int r = 0; r < 32; ++r) {
+      const uint32_t* row = p.pairs_in + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
+      for (int l = lane; l < Lp; l += 32) {
+        const int i = ((l / VW) * 32 + r) * VW + (l % VW);
+        Aw32[i] = (r < cnt) ? row[l] : (l == 0 ? 1u : 0u);
+        Bw32[i] = (r < cnt) ? row[Lp + l] : 0u;
+      }
+    }
+    __syncwarp();
+    pair_mul(R2Ar, R2Br);   // into the Montgomery domain
+
+    // every bucket starts as the Montgomery one
+    for (int s = 0; s < p.nparties * D; ++s) {
+      V* da = slot_a(s); V* db = slot_b(s);
+#pragma unroll 5
+      for (int v = 0; v < LV; ++v) { da[(size_t)v * 32] = ONEAr[(size_t)v * 32]; db[(size_t)v * 32] = ONEBr[(size_t)v * 32]; }
+    }
+
+    for (int k = 0; k < p.nwin; ++k) {
+      if (k > 0) for (int s = 0; s < p.wbits; ++s) pair_sqr();
+      park(CUR);
+      for (int q = 0; q < p.nparties; ++q) {
+        const int s = q * D + (int)p.digits[(size_t)q * p.nwin + k];
+        pair_mul(slot_a(s), slot_b(s));
+        park(s);
+        if (q + 1 < p.nparties || k + 1 < p.nwin) fetch(CUR);
+      }
+    }
+
+    for (int q = 0; q < p.nparties; ++q) {
+      fetch(q * D + D - 1);
+      for (int d = D - 2; d >= 1; --d) {
+        if (d == D - 2) park(ACC);          // S = T = A_{D-1}
+        pair_mul(slot_a(q * D + d), slot_b(q * D + d));   // T <- T * A_d
+        park(CUR);
+        pair_mul(slot_a(ACC), slot_b(ACC));               // S * T
+        park(ACC);
+        if (d > 1) fetch(CUR);
+      }
+      // (D = 2: the single bucket is the result and is already in (A, B); otherwise S is)
+      pair_mul(PLAIN1r, ZEROr);   // out of the Montgomery domain
+      __syncwarp();
+      uint32_t* outp = p.pairs_out + (size_t)q * p.count * (size_t)(2 * Lp);
+      for (int r = 0; r < cnt; ++r) {
+        uint32_t* row = outp + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
+        for (int l = lane; l < Lp; l += 32) {
+          const int i = ((l / VW) * 32 + r) * VW + (l % VW);
+          row[l] = Aw32[i];
+          row[Lp + l] = Bw32[i];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 }  // namespace dkg

@@ -22,4 +22,21 @@ struct NsqParams {
   unsigned int* counter;
 };
 
+// Several exponentiations of the SAME bases (all parties' partial decryptions of one ciphertext
+// batch when their shares sit on one device): one shared squaring chain, per-party digit buckets
+// (modexp_nsq_multi_kernel in dkg_nsq.cuh).
+constexpr int kNsqMultiMaxParties = 8;
+struct NsqMultiParams {
+  const uint32_t* pairs_in;   // [count][2][Lp]
+  uint32_t* pairs_out;        // [nparties][count][2][Lp]
+  unsigned long long count;
+  const uint32_t* consts;     // as NsqParams::consts
+  const uint8_t* digits;      // [nparties][nwin]: |exponent| of party p in base 2^wbits, least significant digit first
+  int nparties, nwin, wbits;
+  uint32_t* scratch;
+  unsigned long long scratch_per_warp;   // in uint32: (nparties * 2^wbits + 2) pairs, then the quotient blocks
+  unsigned long long scratch_q_offset;
+  unsigned int* counter;
+};
+
 }  // namespace dkg
