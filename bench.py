@@ -93,7 +93,7 @@ def hbm_side(traffic_bytes: float, launch_ms: float) -> dict:
 
 # DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) of one launch of the shared-chain
 # kernel on 113 664 ciphertexts x 3 parties, from the committed capture (profiles/); None until captured
-MULTI_TRAFFIC_113664 = None
+MULTI_TRAFFIC_113664 = 381.6e9   # 166.0 GB read + 215.6 GB written (profiles/r02_ncu_multi_traffic.csv)
 
 
 def multi_traffic(B: int):

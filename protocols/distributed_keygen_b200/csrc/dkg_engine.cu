@@ -71,7 +71,11 @@ BatchInvFn lookup_batchinv_group4(int, int); BatchInvFn lookup_batchinv_group5(i
 using NsqFn = void (*)(const NsqParams);
 NsqFn lookup_nsq_group0(int, int); NsqFn lookup_nsq_group1(int, int); NsqFn lookup_nsq_group2(int, int);
 NsqFn lookup_nsq_group3(int, int); NsqFn lookup_nsq_group4(int, int); NsqFn lookup_nsq_group5(int, int);
+NsqFn lookup_nsq_bg_group0(int, int); NsqFn lookup_nsq_bg_group1(int, int); NsqFn lookup_nsq_bg_group2(int, int);
+NsqFn lookup_nsq_bg_group3(int, int); NsqFn lookup_nsq_bg_group4(int, int); NsqFn lookup_nsq_bg_group5(int, int);
 using NsqMultiFn = void (*)(const NsqMultiParams);
+NsqMultiFn lookup_nsq_multi_bg_group0(int, int); NsqMultiFn lookup_nsq_multi_bg_group1(int, int); NsqMultiFn lookup_nsq_multi_bg_group2(int, int);
+NsqMultiFn lookup_nsq_multi_bg_group3(int, int); NsqMultiFn lookup_nsq_multi_bg_group4(int, int); NsqMultiFn lookup_nsq_multi_bg_group5(int, int);
 NsqMultiFn lookup_nsq_multi_group0(int, int); NsqMultiFn lookup_nsq_multi_group1(int, int); NsqMultiFn lookup_nsq_multi_group2(int, int);
 NsqMultiFn lookup_nsq_multi_group3(int, int); NsqMultiFn lookup_nsq_multi_group4(int, int); NsqMultiFn lookup_nsq_multi_group5(int, int);
 using GroupedFn = void (*)(const GroupedParams);
@@ -323,6 +327,7 @@ struct dkg_modexp_ctx {
   uint32_t* d_ops = nullptr;
   // pair arithmetic modulo N when the modulus is N^2 with known N (dkg_nsq.cuh)
   bool nsq = false;
+  bool nsq_bg = false;             // b component in global scratch (wide keys: twice the warps per SM)
   Shape nshape{};
   int nLp = 0, nwarps = 1;
   size_t nsmem = 0, nscratch_per_warp = 0, nscratch_q_offset = 0;
@@ -657,9 +662,19 @@ dkg::NsqFn lookup_nsq(int K, int M) {
   return nullptr;
 }
 
-dkg::NsqMultiFn lookup_nsq_multi(int K, int M) {
-  dkg::NsqMultiFn (*groups[])(int, int) = {dkg::lookup_nsq_multi_group0, dkg::lookup_nsq_multi_group1, dkg::lookup_nsq_multi_group2,
-                                           dkg::lookup_nsq_multi_group3, dkg::lookup_nsq_multi_group4, dkg::lookup_nsq_multi_group5};
+dkg::NsqFn lookup_nsq_bg(int K, int M) {
+  dkg::NsqFn (*groups[])(int, int) = {dkg::lookup_nsq_bg_group0, dkg::lookup_nsq_bg_group1, dkg::lookup_nsq_bg_group2,
+                                      dkg::lookup_nsq_bg_group3, dkg::lookup_nsq_bg_group4, dkg::lookup_nsq_bg_group5};
+  for (auto g : groups)
+    if (dkg::NsqFn f = g(K, M)) return f;
+  return nullptr;
+}
+dkg::NsqMultiFn lookup_nsq_multi(int K, int M, bool bg) {
+  dkg::NsqMultiFn (*plain[])(int, int) = {dkg::lookup_nsq_multi_group0, dkg::lookup_nsq_multi_group1, dkg::lookup_nsq_multi_group2,
+                                          dkg::lookup_nsq_multi_group3, dkg::lookup_nsq_multi_group4, dkg::lookup_nsq_multi_group5};
+  dkg::NsqMultiFn (*wide[])(int, int) = {dkg::lookup_nsq_multi_bg_group0, dkg::lookup_nsq_multi_bg_group1, dkg::lookup_nsq_multi_bg_group2,
+                                         dkg::lookup_nsq_multi_bg_group3, dkg::lookup_nsq_multi_bg_group4, dkg::lookup_nsq_multi_bg_group5};
+  auto& groups = bg ? wide : plain;
   for (auto g : groups)
     if (dkg::NsqMultiFn f = g(K, M)) return f;
   return nullptr;
@@ -667,7 +682,7 @@ dkg::NsqMultiFn lookup_nsq_multi(int K, int M) {
 
 // shapes for the pair components, in order of preference per padded width
 constexpr Shape kNsqShapes[] = {{4, 1}, {4, 2}, {4, 3}, {8, 2}, {6, 3}, {12, 2}, {16, 2}, {12, 3}, {16, 3},
-                                {16, 4}, {14, 5}, {12, 6}, {16, 5}, {16, 6}, {12, 11}, {16, 9}};
+                                {16, 4}, {14, 5}, {12, 6}, {16, 5}, {16, 6}, {14, 7}, {12, 11}, {16, 9}};
 
 }  // namespace
 
@@ -930,14 +945,24 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
 
   const size_t uni = (((size_t)(2 * Lp + K) * 4 + 15) / 16) * 16 +
                      (((size_t)dkg::sched_total_words_closed(sh.M) * 4 + 15) / 16) * 16;  // consts | schedule table
-  const size_t per_warp = (size_t)2 * Lp * 32 * 4;
-  // K = 22 needs more than 168 registers: run it with 10 warps
+  size_t per_warp = (size_t)2 * Lp * 32 * 4;
   int maxw = DKG_MAX_THREADS / 32;
   int warps = (int)std::min<size_t>(maxw, (kMaxDynSmem - uni) / per_warp);
+  // wide keys: shared memory, not registers, caps the warps per SM; with fewer than 10 take the
+  // variant that keeps the b component in global scratch (a only in shared memory)
+  bool bg = false;
+  if (warps < 10 && env_long("DKG_NSQ_BG", 1) != 0) {
+    if (dkg::NsqFn kb = lookup_nsq_bg(sh.K, sh.M)) {
+      kernel = kb; bg = true;
+      per_warp = (size_t)Lp * 32 * 4;
+      warps = (int)std::min<size_t>(maxw, (kMaxDynSmem - uni) / per_warp);
+    }
+  }
   if (warps < 1) return DKG_OK;
   const size_t tsize = (size_t)ctx->tab_entries + 1;  // odd powers, then the slot of c^2
   ctx->nscratch_q_offset = std::max<size_t>(tsize, 1) * 2 * (size_t)Lp * 32;
-  ctx->nscratch_per_warp = ctx->nscratch_q_offset + (size_t)Lp * 32;
+  ctx->nscratch_per_warp = ctx->nscratch_q_offset + (size_t)Lp * 32 * (bg ? 2 : 1);   // Q [| b]
+  ctx->nsq_bg = bg;
   cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(uni + per_warp * warps));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_nconsts, kc.size() * 4);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_nio, ioc.size() * 4);
@@ -1857,11 +1882,11 @@ int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t
   int ebits = 1;
   for (int p = 0; p < shares; ++p) {
     const dkg_modexp_ctx* c = dv.parties[p];
-    if (!c->nsq || !c->use_nsq || c->ct_table || c->nshape.K != c0->nshape.K || c->nshape.M != c0->nshape.M) return DKG_OK;
+    if (!c->nsq || !c->use_nsq || c->ct_table || c->nshape.K != c0->nshape.K || c->nshape.M != c0->nshape.M || c->nsq_bg != c0->nsq_bg) return DKG_OK;
     if (c->negative && c->inv_kernel == nullptr) return DKG_OK;
     ebits = std::max(ebits, c->ebits);
   }
-  dkg::NsqMultiFn kernel = lookup_nsq_multi(c0->nshape.K, c0->nshape.M);
+  dkg::NsqMultiFn kernel = lookup_nsq_multi(c0->nshape.K, c0->nshape.M, c0->nsq_bg);
   if (!kernel) return DKG_OK;
   const size_t slot_words = (size_t)2 * c0->nLp * 32;   // one pair in lane layout
   const size_t total_warps = (size_t)c0->ctas * c0->nwarps;
@@ -1894,7 +1919,7 @@ int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t
   CUDA_TRY(cudaMemcpy(dv.d_digits, digits.data(), digits.size(), cudaMemcpyHostToDevice));
   dv.multi_w = w; dv.multi_nwin = nwin;
   dv.multi_q_offset = (((size_t)shares << w) + 2) * slot_words;
-  dv.multi_scratch_per_warp = dv.multi_q_offset + (size_t)c0->nLp * 32;
+  dv.multi_scratch_per_warp = dv.multi_q_offset + (size_t)c0->nLp * 32 * (c0->nsq_bg ? 2 : 1);   // Q [| b]
   dv.multi_kernel = kernel;
   return DKG_OK;
 }

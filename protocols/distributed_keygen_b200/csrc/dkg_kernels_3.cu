@@ -3,4 +3,5 @@
 #define DKG_GROUP_SHAPES(X) X(20,13) X(16,4) X(16,5)
 #define DKG_GROUP_GROUPED_SHAPES(X) X(16,4) X(16,5)
 #define DKG_GROUP_NSQ_SHAPES(X) X(16,4) X(16,5) X(18,4)
+#define DKG_GROUP_NSQ_BG_SHAPES(X) X(12,11)
 #include "dkg_kernels.inc"

@@ -67,6 +67,20 @@ __device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t o
                : "+r"(r[0]), "+r"(r[1]) : "l"(gp), "r"(on_g), "r"(sp), "r"(on_s) : "memory");
 }
 
+// one predicated load through a generic address (shared or global window)
+__device__ __forceinline__ void ld_pred_generic(uint32_t* r, const char* p, uint32_t on, uint4) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %5, 0;\n\t@pp ld.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"(on) : "memory");
+}
+__device__ __forceinline__ void ld_pred_generic(uint32_t* r, const char* p, uint32_t on, uint2) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %3, 0;\n\t@pp ld.v2.u32 {%0, %1}, [%2];\n\t}"
+               : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"(on) : "memory");
+}
+
+#ifndef DKG_GENERIC_PREFETCH
+#define DKG_GENERIC_PREFETCH 1
+#endif
+
 // IO policy of dkg::mont_mul for one thread of a warp.
 //  xs      shared-space byte address of this lane's vector 0 of X (consecutive vectors of one
 //          lane are 32 vectors apart); ns/nis: the CTA-uniform modulus and block inverse;
@@ -82,8 +96,14 @@ __device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t o
 //          as in the grouped kernel where every lane may have its own modulus.
 //  SCHED   the pair schedule comes from a table in shared memory (sched_s, filled by the kernel
 //          with fill_schedule) instead of being recomputed inside the block-product loop.
-template <int K, int M, bool PLN = false, bool SCHED_ = false>
-struct WarpIO {
+//  XG      X may live in GLOBAL memory instead of shared (xg != nullptr: this lane's vector 0 there,
+//          same vector-major / lane-minor layout; xs is then unused).  The pair kernels of wide keys
+//          keep the b component of the running pair there: with only a in shared memory twice as
+//          many warps fit an SM.  Decided per call (run time), so a and b products share one instance.
+template <class V, bool XG> struct XgField { __device__ __forceinline__ V* xg_get() const { return nullptr; } };
+template <class V> struct XgField<V, true> { V* xg = nullptr; __device__ __forceinline__ V* xg_get() const { return xg; } };
+template <int K, int M, bool PLN = false, bool SCHED_ = false, bool XG_ = false>
+struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
   static constexpr bool SCHED = SCHED_;
   uint32_t sched_s = 0;     // shared-space address of the schedule table (SCHED only)
   __device__ __forceinline__ uint32_t sched_begin(int word_offset) const { return sched_s + 4u * (uint32_t)word_offset; }
@@ -103,11 +123,18 @@ struct WarpIO {
   const V* Y;
   uint32_t ss = 0;          // second shared-memory operand S (pair arithmetic), lane's vector 0
   const V* Y2 = nullptr;    // second global operand (same layout as Y)
+  // (XG only: the member xg of the base class is X's address in global memory, or null)
+  __device__ __forceinline__ bool x_global() const { return XG_ && this->xg_get() != nullptr; }
 
   // never true (a shared-space address is far below 2^32 - 1), but not provably so: guards the
   // pipe-balance ballast in mont_mul
   __device__ __forceinline__ bool never() const { return ns == 0xffffffffu; }
   __device__ __forceinline__ void load_x(int i, uint32_t (&r)[K]) const {
+    if (x_global()) {
+#pragma unroll
+      for (int q = 0; q < KV; q++) { V v; ldg_vec(v, this->xg_get() + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, xs + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
@@ -117,12 +144,14 @@ struct WarpIO {
   }
   // block i of S (from_s) or X: one load sequence for both, the base selected
   __device__ __forceinline__ void load_xs(bool from_s, int i, uint32_t (&r)[K]) const {
+    if (!from_s && x_global()) { load_x(i, r); return; }
     const uint32_t base = from_s ? ss : xs;
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, base + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
   // limb l of X
   __device__ __forceinline__ uint32_t x_limb(int l) const {
+    if (x_global()) return reinterpret_cast<const uint32_t*>(this->xg_get() + (size_t)(l / VW) * 32)[l % VW];
     uint32_t w;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xs + (uint32_t)(l / VW) * 32u * VB + (uint32_t)(l % VW) * 4u));
     return w;
@@ -130,7 +159,7 @@ struct WarpIO {
   // block i of 2*S (from_s) or 2*X: every limb shifted left by one, the bit shifted in is the top
   // bit of the limb below (of block i-1 for the first limb)
   __device__ __forceinline__ void load_xs2(bool from_s, int i, uint32_t (&r)[K]) const {
-    const uint32_t base = from_s ? ss : xs;
+    const uint32_t base = from_s ? ss : xs;   // (the doubled operand is never the global X: SQR runs on a, MUL2S doubles S)
     uint32_t prev = 0;
     if (i > 0) {
       const int l = i * K - 1;
@@ -151,21 +180,48 @@ struct WarpIO {
     for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Qg + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
   }
   // Prefetch descriptor: the next y operand comes either from shared memory (an X block) or from
-  // global memory (table entry / quotient block).  Two predicated loads, exactly one of which is
-  // on, keep the block product branch-free without going through generic addressing.
+  // global memory (table entry / quotient block / the global X of the XG layouts).
+#if DKG_GENERIC_PREFETCH
+  // ONE predicated load through a generic address.  With two predicated loads (ld.global / ld.shared,
+  // exactly one of them on) into the same registers, ptxas sinks the shared-memory ones to the end of
+  // the block product, where each of them -- predicated off or not -- waits on the scoreboard of the
+  // global load still in flight to the same register (write after write): the L2 latency of every
+  // global y operand was exposed once per block product (5 % of all warp stall samples on that one
+  // instruction, profiles/r02_ncu_multi_opcodes.txt).
+  struct Prefetch { const char* base; uint32_t on; };
+  __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
+    Prefetch d;
+    const bool xkind = kind == PAIR_XX || kind == PAIR_XX2 || kind == PAIR_SX2;   // y = a block of X
+    const bool from_shared = xkind && !x_global();
+    d.on = (xkind || kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
+    unsigned long long sgen;
+    asm("cvta.shared.u64 %0, %1;" : "=l"(sgen) : "l"((unsigned long long)(xs + (uint32_t)(blk * KV) * 32u * VB)));
+    const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : ((xkind && x_global()) ? this->xg_get() : Qg));
+    const char* gb = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
+    d.base = from_shared ? reinterpret_cast<const char*>(sgen) : gb;
+    return d;
+  }
+  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
+    ld_pred_generic(&r[v * VW], d.base + (size_t)v * 32u * VB, d.on, V());
+  }
+#else
+  // Two predicated loads, exactly one of which is on, keep the block product branch-free without
+  // going through generic addressing.
   struct Prefetch { const char* gbase; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
-    d.on_s = (kind == PAIR_XX || kind == PAIR_XX2 || kind == PAIR_SX2) ? 1u : 0u;
-    d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
+    const bool xkind = kind == PAIR_XX || kind == PAIR_XX2 || kind == PAIR_SX2;   // y = a block of X
+    d.on_s = (xkind && !x_global()) ? 1u : 0u;
+    d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2 || (xkind && x_global())) ? 1u : 0u;
     d.sbase = xs + (uint32_t)(blk * KV) * 32u * VB;
-    const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : Qg);
+    const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : ((xkind && x_global()) ? this->xg_get() : Qg));
     d.gbase = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
     return d;
   }
   __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
     ld_pred2(&r[v * VW], d.gbase + (size_t)v * 32u * VB, d.on_g, d.sbase + (uint32_t)v * 32u * VB, d.on_s, V());
   }
+#endif
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, ns + (uint32_t)(j * KV + q) * NSTRIDE); unpack(v, &r[q * VW]); }
@@ -179,6 +235,11 @@ struct WarpIO {
     for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); stg_vec(Qg + (size_t)(i * KV + q) * 32, v); }
   }
   __device__ __forceinline__ void store_x(int i, const uint32_t (&r)[K]) const {
+    if (x_global()) {
+#pragma unroll
+      for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); stg_vec(this->xg_get() + (size_t)(i * KV + q) * 32, v); }
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); sts_vec(xs + (uint32_t)(i * KV + q) * 32u * VB, v); }
   }
@@ -284,13 +345,13 @@ __device__ uint32_t mod_inverse_lane(uint32_t* X, const uint32_t* Ns, uint32_t n
 
 // One out-of-line instance of the Montgomery product per shape, shared by every mode (square,
 // multiply, reduce, doubled product, multiply-add): the hot loop stays inside the instruction cache.
-template <int K, int M, bool PLN, bool SCHED>
-__device__ __noinline__ void mont_call_rt(const WarpIO<K, M, PLN, SCHED> io, const int mode) {
+template <int K, int M, bool PLN, bool SCHED, bool XG>
+__device__ __noinline__ void mont_call_rt(const WarpIO<K, M, PLN, SCHED, XG> io, const int mode) {
   mont_mul<K, M>(io, mode);
 }
-template <int K, int M, int MODE, bool PLN = false, bool SCHED = false>
-__device__ __forceinline__ void mont_call(const WarpIO<K, M, PLN, SCHED>& io) {
-  mont_call_rt<K, M, PLN, SCHED>(io, MODE);
+template <int K, int M, int MODE, bool PLN = false, bool SCHED = false, bool XG = false>
+__device__ __forceinline__ void mont_call(const WarpIO<K, M, PLN, SCHED, XG>& io) {
+  mont_call_rt<K, M, PLN, SCHED, XG>(io, MODE);
 }
 // all threads of the CTA fill the schedule table (sched_offset<M>(kSchedModes) words at `tab`)
 template <int M>

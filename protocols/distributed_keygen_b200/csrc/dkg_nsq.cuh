@@ -86,7 +86,10 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const type
 template <int M>
 constexpr int kNsqSchedWords = sched_offset<M>(kSchedModes);
 
-template <int K, int M>
+// BG: the b component of the running pair lives in the warp's GLOBAL scratch (after the quotient
+// blocks, L2 resident) instead of shared memory, which then holds a only: twice as many warps per SM
+// for wide keys (6 -> 12 at key_length 4096), where shared memory, not registers, caps the occupancy.
+template <int K, int M, bool BG = false>
 __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const NsqParams p) {
   static_assert(kNsqSchedWords<M> == sched_total_words_closed(M), "schedule table size: host formula out of sync with ColPlan");
   using V = typename VecSel<K>::T;
@@ -106,10 +109,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   const uint32_t* Ns32 = U32;
   const uint32_t* Dneg = U32 + Lp + K;
 
-  V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * 2 * LV * 32;
-  V* Bw = Aw + LV * 32;
+  V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * (BG ? 1 : 2) * LV * 32;
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
-  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
   const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
   const V* ONEA = Cg + 2 * LV, *ONEB = Cg + 3 * LV;
   // the six constants again, lane-replicated ([v][lane]) so that they can be multiplication operands
@@ -122,10 +123,12 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
   V* tab = reinterpret_cast<V*>(scratch32);   // entry d (1-based): a at ((d-1)*2)*LV*32, b right after
   V* Qg = reinterpret_cast<V*>(scratch32 + p.scratch_q_offset);
+  V* Bw = BG ? Qg + LV * 32 : Aw + LV * 32;
+  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
 
   const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(Aw + lane);
-  const uint32_t b_s = (uint32_t)__cvta_generic_to_shared(Bw + lane);
-  WarpIO<K, M, false, true> io;
+  const uint32_t b_s = BG ? 0u : (uint32_t)__cvta_generic_to_shared(Bw + lane);
+  WarpIO<K, M, false, true, BG> io;
   io.sched_s = (uint32_t)__cvta_generic_to_shared(smem_raw + UNI0);
   io.ns = (uint32_t)__cvta_generic_to_shared(Ns32);
   io.nis = (uint32_t)__cvta_generic_to_shared(Ns32 + Lp);
@@ -134,16 +137,20 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   // (A, B) <- (A, B) * (c, d): c, d in global memory, lane layout
   auto pair_mul = [&](const V* c, const V* d) {
     io.xs = b_s; io.ss = a_s; io.Y = c; io.Y2 = d;
-    mont_call<K, M, MONT_MULADD, false, true>(io);                 // B <- REDC(B c + A d)
+    if constexpr (BG) io.xg = Bw + lane;
+    mont_call<K, M, MONT_MULADD, false, true, BG>(io);             // B <- REDC(B c + A d)
     io.xs = a_s;
-    mont_call<K, M, MONT_MUL, false, true>(io);                    // A <- REDC(A c), quotient m in Q
+    if constexpr (BG) io.xg = nullptr;
+    mont_call<K, M, MONT_MUL, false, true, BG>(io);                // A <- REDC(A c), quotient m in Q
     pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
   };
   auto pair_sqr = [&]() {
     io.xs = b_s; io.ss = a_s;
-    mont_call<K, M, MONT_MUL2S, false, true>(io);                  // B <- REDC(2 B A)
+    if constexpr (BG) io.xg = Bw + lane;
+    mont_call<K, M, MONT_MUL2S, false, true, BG>(io);              // B <- REDC(2 B A)
     io.xs = a_s;
-    mont_call<K, M, MONT_SQR, false, true>(io);                    // A <- REDC(A^2), quotient m in Q
+    if constexpr (BG) io.xg = nullptr;
+    mont_call<K, M, MONT_SQR, false, true, BG>(io);                // A <- REDC(A^2), quotient m in Q
     pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
   };
 
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
 // The Montgomery product overwrites its shared-memory operand, so the running power is parked in
 // the warp's global scratch around every bucket multiplication (2 P + 1 copies of 2 Lp limbs per
 // window against 6 squarings + P multiplications: < 1 % of the instructions).
-template <int K, int M>
+template <int K, int M, bool BG = false>
 __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(const NsqMultiParams p) {
   using V = typename VecSel<K>::T;
   constexpr int VW = VecSel<K>::VW;
@@ -284,10 +291,8 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
   const uint32_t* Ns32 = U32;
   const uint32_t* Dneg = U32 + Lp + K;
 
-  V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * 2 * LV * 32;
-  V* Bw = Aw + LV * 32;
+  V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * (BG ? 1 : 2) * LV * 32;
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
-  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
   const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
   const V* Crep = Cg + 6 * LV + lane;
   const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
@@ -298,14 +303,16 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
   V* slots = reinterpret_cast<V*>(scratch32);   // pair s: a at (2s)*LV*32, b right after
   V* Qg = reinterpret_cast<V*>(scratch32 + p.scratch_q_offset);
+  V* Bw = BG ? Qg + LV * 32 : Aw + LV * 32;
+  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
   const int D = 1 << p.wbits;
   auto slot_a = [&](int s) -> V* { return slots + (size_t)s * 2 * LV * 32 + lane; };
   auto slot_b = [&](int s) -> V* { return slots + ((size_t)s * 2 + 1) * LV * 32 + lane; };
   const int CUR = p.nparties * D, ACC = CUR + 1;   // parked running power / bucket accumulator S
 
   const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(Aw + lane);
-  const uint32_t b_s = (uint32_t)__cvta_generic_to_shared(Bw + lane);
-  WarpIO<K, M, false, true> io;
+  const uint32_t b_s = BG ? 0u : (uint32_t)__cvta_generic_to_shared(Bw + lane);
+  WarpIO<K, M, false, true, BG> io;
   io.sched_s = (uint32_t)__cvta_generic_to_shared(smem_raw + UNI0);
   io.ns = (uint32_t)__cvta_generic_to_shared(Ns32);
   io.nis = (uint32_t)__cvta_generic_to_shared(Ns32 + Lp);
@@ -313,16 +320,20 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
 
   auto pair_mul = [&](const V* c, const V* d) {
     io.xs = b_s; io.ss = a_s; io.Y = c; io.Y2 = d;
-    mont_call<K, M, MONT_MULADD, false, true>(io);
+    if constexpr (BG) io.xg = Bw + lane;
+    mont_call<K, M, MONT_MULADD, false, true, BG>(io);
     io.xs = a_s;
-    mont_call<K, M, MONT_MUL, false, true>(io);
+    if constexpr (BG) io.xg = nullptr;
+    mont_call<K, M, MONT_MUL, false, true, BG>(io);
     pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
   };
   auto pair_sqr = [&]() {
     io.xs = b_s; io.ss = a_s;
-    mont_call<K, M, MONT_MUL2S, false, true>(io);
+    if constexpr (BG) io.xg = Bw + lane;
+    mont_call<K, M, MONT_MUL2S, false, true, BG>(io);
     io.xs = a_s;
-    mont_call<K, M, MONT_SQR, false, true>(io);
+    if constexpr (BG) io.xg = nullptr;
+    mont_call<K, M, MONT_SQR, false, true, BG>(io);
     pair_fixup<K, M>(Bw + lane, Qg + lane, Ns32, Dneg);
   };
   auto park = [&](int s) {      // slot s <- (A, B)

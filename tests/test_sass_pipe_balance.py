@@ -2,8 +2,8 @@
 function whether register moves and carry adds go to the ALU pipe (MOV, IADD3.X) or to the multiplier
 pipe (IMAD.MOV.U32, IMAD.X) -- the one pipe the exponentiation saturates.  A compiler change that
 undoes the ballast's effect would silently cost ~5-15 % throughput; this test fails loudly instead.
-Checked on the SASS of the headline kernel, modexp_nsq_kernel<14,5>, inside its noinline Montgomery
-product (the target of its CALLs)."""
+Checked on the SASS of the headline kernels, modexp_nsq_kernel<14,5> and modexp_nsq_multi_kernel<14,5>,
+inside their noinline Montgomery product (the target of their CALLs)."""
 from __future__ import annotations
 
 import collections
@@ -13,10 +13,12 @@ import subprocess
 
 import pytest
 
-KERNEL = "_ZN3dkg17modexp_nsq_kernelILi14ELi5EEEvNS_9NsqParamsE"
+KERNELS = ["_ZN3dkg17modexp_nsq_kernelILi14ELi5ELb0EEEvNS_9NsqParamsE",
+           "_ZN3dkg23modexp_nsq_multi_kernelILi14ELi5ELb0EEEvNS_14NsqMultiParamsE"]
 
 
-def test_hot_montgomery_product_keeps_the_multiplier_pipe_for_multiplies():
+@pytest.mark.parametrize("KERNEL", KERNELS)
+def test_hot_montgomery_product_keeps_the_multiplier_pipe_for_multiplies(KERNEL):
     from protocols.distributed_keygen_b200 import _native
 
     if shutil.which("cuobjdump") is None:
