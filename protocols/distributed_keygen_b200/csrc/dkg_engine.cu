@@ -329,7 +329,7 @@ struct dkg_modexp_ctx {
   bool nsq = false;
   bool nsq_bg = false;             // b component in global scratch (wide keys: twice the warps per SM)
   Shape nshape{};
-  int nLp = 0, nwarps = 1;
+  int nLp = 0, nLs = 0, nwarps = 1;   // dense / slot-layout limbs of a pair component
   size_t nsmem = 0, nscratch_per_warp = 0, nscratch_q_offset = 0;
   uint32_t n_n0inv = 0;
   dkg::NsqFn nsq_kernel = nullptr;
@@ -682,7 +682,7 @@ dkg::NsqMultiFn lookup_nsq_multi(int K, int M, bool bg) {
 
 // shapes for the pair components, in order of preference per padded width
 constexpr Shape kNsqShapes[] = {{4, 1}, {4, 2}, {4, 3}, {8, 2}, {6, 3}, {12, 2}, {16, 2}, {12, 3}, {16, 3},
-                                {16, 4}, {14, 5}, {12, 6}, {16, 5}, {16, 6}, {14, 7}, {12, 11}, {16, 9}};
+                                {16, 4}, {13, 5}, {14, 5}, {12, 6}, {16, 5}, {16, 6}, {14, 7}, {12, 11}, {16, 9}};
 
 }  // namespace
 
@@ -903,7 +903,15 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
     for (const Shape& c : kNsqShapes)
       if (c.K * c.M >= need && (kernel = lookup_nsq(c.K, c.M)) != nullptr) { sh = c; break; }
   if (!kernel || sh.K * sh.M > dkg::kNsqMaxL) return DKG_OK;  // too wide: keep the direct kernel
-  const int Lp = sh.K * sh.M, K = sh.K;
+  // Lp: limbs of the pair components, R = 2^(32 Lp).  In the kernel's memory a block of K limbs
+  // occupies a slot of KP = K + (K & 1) limbs (whole 64-bit vectors; odd K: one zero pad limb), a
+  // number Ls = KP * M limbs; the entry / exit kernels and the pair rows between them are dense (Lp).
+  const int Lp = sh.K * sh.M, K = sh.K, KP = K + (K & 1), Ls = KP * sh.M;
+  auto slotted = [&](const dkg_host::Limbs& v) {
+    dkg_host::Limbs out((size_t)KP * (v.size() / K), 0);
+    for (size_t i = 0; i < v.size(); ++i) out[(i / K) * KP + i % K] = v[i];
+    return out;
+  };
   dkg_host::Limbs N(Lp, 0);
   for (int i = 0; i < ln; ++i) N[i] = nn[i];
   dkg_host::Limbs ninv = dkg_host::neg_inv_block(N, K);
@@ -938,14 +946,17 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
   dkg_host::Limbs plain1(Lp, 0), zero(Lp, 0);
   plain1[0] = 1;
   std::vector<uint32_t> kc;
-  for (const dkg_host::Limbs* v : {&N, &ninv, &dneg, &r2a, &r2b, &onea, &oneb, &plain1, &zero}) kc.insert(kc.end(), v->begin(), v->end());
-  for (const dkg_host::Limbs* v : {&r2a, &r2b, &onea, &oneb, &plain1, &zero}) append_lane_replicated(kc, *v, K);
+  for (const dkg_host::Limbs* v : {&N, &ninv, &dneg, &r2a, &r2b, &onea, &oneb, &plain1, &zero}) {
+    const dkg_host::Limbs sv = slotted(*v);
+    kc.insert(kc.end(), sv.begin(), sv.end());
+  }
+  for (const dkg_host::Limbs* v : {&r2a, &r2b, &onea, &oneb, &plain1, &zero}) append_lane_replicated(kc, slotted(*v), KP);
   std::vector<uint32_t> ioc;
   for (const dkg_host::Limbs* v : {&N, &r2_mod_n, &ninvpos}) ioc.insert(ioc.end(), v->begin(), v->end());
 
-  const size_t uni = (((size_t)(2 * Lp + K) * 4 + 15) / 16) * 16 +
+  const size_t uni = (((size_t)(2 * Ls + KP) * 4 + 15) / 16) * 16 +
                      (((size_t)dkg::sched_total_words_closed(sh.M) * 4 + 15) / 16) * 16;  // consts | schedule table
-  size_t per_warp = (size_t)2 * Lp * 32 * 4;
+  size_t per_warp = (size_t)2 * Ls * 32 * 4;
   int maxw = DKG_MAX_THREADS / 32;
   int warps = (int)std::min<size_t>(maxw, (kMaxDynSmem - uni) / per_warp);
   // wide keys: shared memory, not registers, caps the warps per SM; with fewer than 10 take the
@@ -954,14 +965,14 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
   if (warps < 10 && env_long("DKG_NSQ_BG", 1) != 0) {
     if (dkg::NsqFn kb = lookup_nsq_bg(sh.K, sh.M)) {
       kernel = kb; bg = true;
-      per_warp = (size_t)Lp * 32 * 4;
+      per_warp = (size_t)Ls * 32 * 4;
       warps = (int)std::min<size_t>(maxw, (kMaxDynSmem - uni) / per_warp);
     }
   }
   if (warps < 1) return DKG_OK;
   const size_t tsize = (size_t)ctx->tab_entries + 1;  // odd powers, then the slot of c^2
-  ctx->nscratch_q_offset = std::max<size_t>(tsize, 1) * 2 * (size_t)Lp * 32;
-  ctx->nscratch_per_warp = ctx->nscratch_q_offset + (size_t)Lp * 32 * (bg ? 2 : 1);   // Q [| b]
+  ctx->nscratch_q_offset = std::max<size_t>(tsize, 1) * 2 * (size_t)Ls * 32;
+  ctx->nscratch_per_warp = ctx->nscratch_q_offset + (size_t)Ls * 32 * (bg ? 2 : 1);   // Q [| b]
   ctx->nsq_bg = bg;
   cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(uni + per_warp * warps));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_nconsts, kc.size() * 4);
@@ -973,7 +984,7 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
     *out = nullptr;
     return fail(DKG_ERR_CUDA, std::string("nsq context: ") + cudaGetErrorString(e));
   }
-  ctx->nshape = sh; ctx->nLp = Lp; ctx->nwarps = warps; ctx->nsmem = uni + per_warp * warps;
+  ctx->nshape = sh; ctx->nLp = Lp; ctx->nLs = Ls; ctx->nwarps = warps; ctx->nsmem = uni + per_warp * warps;
   ctx->n_n0inv = ninv[0]; ctx->nsq_kernel = kernel; ctx->nsq = true;
 
   // ---- cooperative (warp-per-operand) latency path, dkg_coop.cuh: its own R = 2^(32 cLc) >= 8N -----
@@ -1888,7 +1899,7 @@ int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t
   }
   dkg::NsqMultiFn kernel = lookup_nsq_multi(c0->nshape.K, c0->nshape.M, c0->nsq_bg);
   if (!kernel) return DKG_OK;
-  const size_t slot_words = (size_t)2 * c0->nLp * 32;   // one pair in lane layout
+  const size_t slot_words = (size_t)2 * c0->nLs * 32;   // one pair in lane layout
   const size_t total_warps = (size_t)c0->ctas * c0->nwarps;
   const size_t cap_words = (size_t)env_long("DKG_MULTI_SCRATCH_MB", 24576) * (1u << 18);
   int best = 0;
@@ -1919,7 +1930,7 @@ int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t
   CUDA_TRY(cudaMemcpy(dv.d_digits, digits.data(), digits.size(), cudaMemcpyHostToDevice));
   dv.multi_w = w; dv.multi_nwin = nwin;
   dv.multi_q_offset = (((size_t)shares << w) + 2) * slot_words;
-  dv.multi_scratch_per_warp = dv.multi_q_offset + (size_t)c0->nLp * 32 * (c0->nsq_bg ? 2 : 1);   // Q [| b]
+  dv.multi_scratch_per_warp = dv.multi_q_offset + (size_t)c0->nLs * 32 * (c0->nsq_bg ? 2 : 1);   // Q [| b]
   dv.multi_kernel = kernel;
   return DKG_OK;
 }

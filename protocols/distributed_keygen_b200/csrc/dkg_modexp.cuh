@@ -77,6 +77,13 @@ __device__ __forceinline__ void ld_pred_generic(uint32_t* r, const char* p, uint
                : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"(on) : "memory");
 }
 
+__device__ __forceinline__ void ld_generic(uint4& v, const char* p) {
+  asm volatile("ld.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ld_generic(uint2& v, const char* p) {
+  asm volatile("ld.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+}
+
 #ifndef DKG_GENERIC_PREFETCH
 #define DKG_GENERIC_PREFETCH 1
 #endif
@@ -103,7 +110,7 @@ __device__ __forceinline__ void ld_pred_generic(uint32_t* r, const char* p, uint
 template <class V, bool XG> struct XgField { __device__ __forceinline__ V* xg_get() const { return nullptr; } };
 template <class V> struct XgField<V, true> { V* xg = nullptr; __device__ __forceinline__ V* xg_get() const { return xg; } };
 template <int K, int M, bool PLN = false, bool SCHED_ = false, bool XG_ = false>
-struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
+struct WarpIO : XgField<typename VecSel<kpad<K>>::T, XG_> {
   static constexpr bool SCHED = SCHED_;
   uint32_t sched_s = 0;     // shared-space address of the schedule table (SCHED only)
   __device__ __forceinline__ uint32_t sched_begin(int word_offset) const { return sched_s + 4u * (uint32_t)word_offset; }
@@ -113,9 +120,11 @@ struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + 4u * (uint32_t)i));
     return w;
   }
-  using V = typename VecSel<K>::T;
-  static constexpr int VW = VecSel<K>::VW;
-  static constexpr int KV = K / VW;
+  // blocks sit in slots of KP = K + (K & 1) limbs (whole vectors; the pad limb of an odd K is zero)
+  static constexpr int KP = kpad<K>;
+  using V = typename VecSel<KP>::T;
+  static constexpr int VW = VecSel<KP>::VW;
+  static constexpr int KV = KP / VW;
   static constexpr uint32_t VB = sizeof(V);
   static constexpr uint32_t NSTRIDE = PLN ? 32u * VB : VB;
   uint32_t xs, ns, nis;
@@ -129,7 +138,7 @@ struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
   // never true (a shared-space address is far below 2^32 - 1), but not provably so: guards the
   // pipe-balance ballast in mont_mul
   __device__ __forceinline__ bool never() const { return ns == 0xffffffffu; }
-  __device__ __forceinline__ void load_x(int i, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_x(int i, uint32_t (&r)[KP]) const {
     if (x_global()) {
 #pragma unroll
       for (int q = 0; q < KV; q++) { V v; ldg_vec(v, this->xg_get() + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
@@ -138,32 +147,33 @@ struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, xs + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
-  __device__ __forceinline__ void load_s(int i, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_s(int i, uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, ss + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
   // block i of S (from_s) or X: one load sequence for both, the base selected
-  __device__ __forceinline__ void load_xs(bool from_s, int i, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_xs(bool from_s, int i, uint32_t (&r)[KP]) const {
     if (!from_s && x_global()) { load_x(i, r); return; }
     const uint32_t base = from_s ? ss : xs;
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, base + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
   }
-  // limb l of X
-  __device__ __forceinline__ uint32_t x_limb(int l) const {
-    if (x_global()) return reinterpret_cast<const uint32_t*>(this->xg_get() + (size_t)(l / VW) * 32)[l % VW];
+  // top limb (K - 1) of block b of X
+  __device__ __forceinline__ uint32_t x_top_limb(int b) const {
+    constexpr int tv = (K - 1) / VW, te = (K - 1) % VW;
+    if (x_global()) return reinterpret_cast<const uint32_t*>(this->xg_get() + (size_t)(b * KV + tv) * 32)[te];
     uint32_t w;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xs + (uint32_t)(l / VW) * 32u * VB + (uint32_t)(l % VW) * 4u));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(xs + (uint32_t)(b * KV + tv) * 32u * VB + (uint32_t)te * 4u));
     return w;
   }
   // block i of 2*S (from_s) or 2*X: every limb shifted left by one, the bit shifted in is the top
   // bit of the limb below (of block i-1 for the first limb)
-  __device__ __forceinline__ void load_xs2(bool from_s, int i, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_xs2(bool from_s, int i, uint32_t (&r)[KP]) const {
     const uint32_t base = from_s ? ss : xs;   // (the doubled operand is never the global X: SQR runs on a, MUL2S doubles S)
     uint32_t prev = 0;
     if (i > 0) {
-      const int l = i * K - 1;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(prev) : "r"(base + (uint32_t)(l / VW) * 32u * VB + (uint32_t)(l % VW) * 4u));
+      constexpr int tv = (K - 1) / VW, te = (K - 1) % VW;   // top limb of block i - 1
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(prev) : "r"(base + (uint32_t)((i - 1) * KV + tv) * 32u * VB + (uint32_t)te * 4u));
     }
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, base + (uint32_t)(i * KV + q) * 32u * VB); unpack(v, &r[q * VW]); }
@@ -171,11 +181,11 @@ struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
     for (int p = K - 1; p > 0; p--) r[p] = __funnelshift_l(r[p - 1], r[p], 1);
     r[0] = __funnelshift_l(prev, r[0], 1);
   }
-  __device__ __forceinline__ void load_y(int j, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_y(int j, uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Y + (size_t)(j * KV + q) * 32); unpack(v, &r[q * VW]); }
   }
-  __device__ __forceinline__ void load_q(int i, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_q(int i, uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; ldg_vec(v, Qg + (size_t)(i * KV + q) * 32); unpack(v, &r[q * VW]); }
   }
@@ -188,21 +198,26 @@ struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
   // global load still in flight to the same register (write after write): the L2 latency of every
   // global y operand was exposed once per block product (5 % of all warp stall samples on that one
   // instruction, profiles/r02_ncu_multi_opcodes.txt).
-  struct Prefetch { const char* base; uint32_t on; };
+  // The load is unconditional: a step without a y operand (the quotient step, the end of the product)
+  // reads a valid dummy (shared memory, short latency) into registers that are overwritten before
+  // their next use -- no predicate to set up and to keep alive through the block product.
+  struct Prefetch { const char* base; };
   __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
     Prefetch d;
     const bool xkind = kind == PAIR_XX || kind == PAIR_XX2 || kind == PAIR_SX2;   // y = a block of X
     const bool from_shared = xkind && !x_global();
-    d.on = (xkind || kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2) ? 1u : 0u;
+    const bool none = !(xkind || kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2);
     unsigned long long sgen;
-    asm("cvta.shared.u64 %0, %1;" : "=l"(sgen) : "l"((unsigned long long)(xs + (uint32_t)(blk * KV) * 32u * VB)));
+    asm("cvta.shared.u64 %0, %1;" : "=l"(sgen) : "l"((unsigned long long)((none ? ns : xs) + (uint32_t)((none ? 0 : blk) * KV) * 32u * VB)));
     const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : ((xkind && x_global()) ? this->xg_get() : Qg));
     const char* gb = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
-    d.base = from_shared ? reinterpret_cast<const char*>(sgen) : gb;
+    d.base = (from_shared || none) ? reinterpret_cast<const char*>(sgen) : gb;
     return d;
   }
-  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
-    ld_pred_generic(&r[v * VW], d.base + (size_t)v * 32u * VB, d.on, V());
+  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[KP]) const {
+    V val;
+    ld_generic(val, d.base + (size_t)v * 32u * VB);
+    unpack(val, &r[v * VW]);
   }
 #else
   // Two predicated loads, exactly one of which is on, keep the block product branch-free without
@@ -218,23 +233,23 @@ struct WarpIO : XgField<typename VecSel<K>::T, XG_> {
     d.gbase = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
     return d;
   }
-  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[KP]) const {
     ld_pred2(&r[v * VW], d.gbase + (size_t)v * 32u * VB, d.on_g, d.sbase + (uint32_t)v * 32u * VB, d.on_s, V());
   }
 #endif
-  __device__ __forceinline__ void load_n(int j, uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_n(int j, uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, ns + (uint32_t)(j * KV + q) * NSTRIDE); unpack(v, &r[q * VW]); }
   }
-  __device__ __forceinline__ void load_ninv(uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void load_ninv(uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, nis + (uint32_t)q * NSTRIDE); unpack(v, &r[q * VW]); }
   }
-  __device__ __forceinline__ void store_q(int i, const uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void store_q(int i, const uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); stg_vec(Qg + (size_t)(i * KV + q) * 32, v); }
   }
-  __device__ __forceinline__ void store_x(int i, const uint32_t (&r)[K]) const {
+  __device__ __forceinline__ void store_x(int i, const uint32_t (&r)[KP]) const {
     if (x_global()) {
 #pragma unroll
       for (int q = 0; q < KV; q++) { V v; pack(v, &r[q * VW]); stg_vec(this->xg_get() + (size_t)(i * KV + q) * 32, v); }

@@ -57,12 +57,21 @@ DKG_HD uint32_t pipe_ballast(uint32_t a, uint32_t b) {
 // i+j odd (aligned at odd limbs); the carry out of every row chain is counted in CE/CO instead of
 // being rippled through the upper limbs, so rows stay independent and nothing is merged inside
 // the inner loop.  `merge` folds everything back into E (once or twice per column).
+// K may be odd (a 2048-bit-class N needs 65 limbs: 5 blocks of 13 instead of 5 of 14 saves 14 % of
+// the multiplications).  Operand blocks then sit in slots of KP = K + 1 limbs (whole 64-bit vectors),
+// the pad limb zero and never multiplied.  Carry counters by limb position: CE[k] weighs limb
+// KP + 2k (the even positions from K up), CO[k] limb KO + 2k (the odd ones), KO = K + 1 - (K & 1).
+template <int K> constexpr int kpad = K + (K & 1);          // slot size in limbs
+template <int K> constexpr int kodd0 = K + 1 - (K & 1);     // first odd limb position >= K
+template <int K> constexpr int kncE = (2 * K - kpad<K>) / 2 + 1;
+template <int K> constexpr int kncO = (2 * K - 1 - kodd0<K>) / 2 + 1;
+
 template <int K>
 struct ColAcc {
   uint64_t E[K + 1];   // limbs (2p, 2p+1)
   uint64_t O[K - 1];   // limbs (2p+1, 2p+2)
-  uint32_t CE[K / 2 + 1];
-  uint32_t CO[K / 2];
+  uint32_t CE[kncE<K>];
+  uint32_t CO[kncO<K>];
 };
 
 template <int K>
@@ -70,9 +79,9 @@ DKG_HD void acc_clear_side(ColAcc<K>& a) {
 #pragma unroll
   for (int i = 0; i < K - 1; i++) a.O[i] = 0;
 #pragma unroll
-  for (int i = 0; i < K / 2 + 1; i++) a.CE[i] = 0;
+  for (int i = 0; i < kncE<K>; i++) a.CE[i] = 0;
 #pragma unroll
-  for (int i = 0; i < K / 2; i++) a.CO[i] = 0;
+  for (int i = 0; i < kncO<K>; i++) a.CO[i] = 0;
 }
 
 // Operand kinds of a block product, also the source selector of the prefetch:
@@ -98,33 +107,32 @@ struct PairDesc {
 // the L2/global latency of Q blocks and table entries hides under the ~1000 multiplier cycles of
 // this product.
 template <int K, class IO>
-DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[K], uint32_t (&y)[K], const IO& io,
+DKG_HD void block_mac(ColAcc<K>& a, const uint32_t (&x)[kpad<K>], uint32_t (&y)[kpad<K>], const IO& io,
                       const typename IO::Prefetch& pf) {
-  static_assert(K % 2 == 0 && K >= 4, "K must be even and >= 4");
+  static_assert(K >= 4, "K must be >= 4");
   constexpr int VW = IO::VW;
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    if ((j & 1) == 0) {
-      mad_cc64(a.E[j / 2], x[0], y[j]);
+    // even positions i + j: chain into E, its carry out counted at limb (last i) + j + 2
+    {
+      const int i0 = j & 1;
+      const int last = ((K - 1 - i0) & 1) ? K - 2 : K - 1;
+      mad_cc64(a.E[(i0 + j) / 2], x[i0], y[j]);
 #pragma unroll
-      for (int i = 2; i < K; i += 2) madc_cc64(a.E[(i + j) / 2], x[i], y[j]);
-      addc(a.CE[j / 2], 0);  // limb j+K
-      mad_cc64(a.O[j / 2], x[1], y[j]);
+      for (int i = i0 + 2; i < last; i += 2) madc_cc64(a.E[(i + j) / 2], x[i], y[j]);
+      madc_cc64_count(a.E[(last + j) / 2], x[last], y[j], a.CE[(last + j + 2 - kpad<K>) / 2]);
+    }
+    // odd positions: chain into O (O[q] holds limbs (2q+1, 2q+2))
+    {
+      const int i0 = (j & 1) ^ 1;
+      const int last = ((K - 1 - i0) & 1) ? K - 2 : K - 1;
+      mad_cc64(a.O[(i0 + j - 1) / 2], x[i0], y[j]);
 #pragma unroll
-      for (int i = 3; i < K; i += 2) madc_cc64(a.O[(i + j - 1) / 2], x[i], y[j]);
-      addc(a.CO[j / 2], 0);  // O limb j+K
-    } else {
-      mad_cc64(a.E[(j + 1) / 2], x[1], y[j]);
-#pragma unroll
-      for (int i = 3; i < K; i += 2) madc_cc64(a.E[(i + j) / 2], x[i], y[j]);
-      addc(a.CE[(j + 1) / 2], 0);  // limb j+K+1
-      mad_cc64(a.O[(j - 1) / 2], x[0], y[j]);
-#pragma unroll
-      for (int i = 2; i < K; i += 2) madc_cc64(a.O[(i + j - 1) / 2], x[i], y[j]);
-      addc(a.CO[(j - 1) / 2], 0);  // O limb j+K-1
+      for (int i = i0 + 2; i < last; i += 2) madc_cc64(a.O[(i + j - 1) / 2], x[i], y[j]);
+      madc_cc64_count(a.O[(last + j - 1) / 2], x[last], y[j], a.CO[(last + j + 2 - kodd0<K>) / 2]);
     }
     // one predicated load, no branch: the block product stays a single basic block
-    if ((j + 1) % VW == 0) io.prefetch_load(pf, (j + 1) / VW - 1, y);
+    if ((j + 1) % VW == 0 || j == K - 1) io.prefetch_load(pf, j / VW, y);
   }
 }
 
@@ -143,13 +151,13 @@ DKG_HD void acc_merge(ColAcc<K>& a, uint32_t (&e)[2 * K + 2]) {
   addc_cc(e[2 * K - 1], 0);
   addc_cc(e[2 * K], 0);
   addc(e[2 * K + 1], 0);
-  add_cc(e[K], a.CE[0]);
+  // the carry counters, one chain over the limbs K .. 2K (even positions: CE, odd ones: CO)
 #pragma unroll
-  for (int k = 0; k < K / 2; k++) {
-    if (k > 0) addc_cc(e[K + 2 * k], a.CE[k]);
-    addc_cc(e[K + 2 * k + 1], a.CO[k]);
+  for (int p = K; p <= 2 * K; p++) {
+    const bool even = ((p - kpad<K>) & 1) == 0;
+    const uint32_t cnt = even ? a.CE[(p - kpad<K>) / 2] : a.CO[(p - kodd0<K>) / 2];
+    if (p == K) add_cc(e[p], cnt); else addc_cc(e[p], cnt);
   }
-  addc_cc(e[2 * K], a.CE[K / 2]);
   addc(e[2 * K + 1], 0);
   acc_clear_side<K>(a);
 }
@@ -157,16 +165,18 @@ DKG_HD void acc_merge(ColAcc<K>& a, uint32_t (&e)[2 * K + 2]) {
 // low block of the accumulated value: (E + (O << 32)) mod 2^(32K); a is not modified
 template <int K>
 DKG_HD void acc_low(const ColAcc<K>& a, uint32_t (&tl)[K]) {
+  uint32_t t[kpad<K>], o[kpad<K>];  // O limbs 0..K-2 (O limb q sits at limb position q+1)
 #pragma unroll
-  for (int p = 0; p < K / 2; p++) unpack64(a.E[p], tl[2 * p], tl[2 * p + 1]);
-  uint32_t o[K];  // O limbs 0..K-1 (O limb q sits at limb position q+1)
+  for (int p = 0; p < (K + 1) / 2; p++) unpack64(a.E[p], t[2 * p], t[2 * p + 1]);
 #pragma unroll
   for (int p = 0; p < K / 2; p++) unpack64(a.O[p], o[2 * p], o[2 * p + 1]);
-  add_cc(tl[1], o[0]);
+  add_cc(t[1], o[0]);
 #pragma unroll
   for (int p = 2; p < K; p++) {
-    if (p < K - 1) addc_cc(tl[p], o[p - 1]); else addc(tl[p], o[p - 1]);
+    if (p < K - 1) addc_cc(t[p], o[p - 1]); else addc(t[p], o[p - 1]);
   }
+#pragma unroll
+  for (int p = 0; p < K; p++) tl[p] = t[p];
 }
 
 template <int K>
@@ -175,35 +185,34 @@ DKG_HD void acc_load(ColAcc<K>& a, const uint32_t (&e)[2 * K + 2]) {
   for (int p = 0; p < K + 1; p++) a.E[p] = pack64(e[2 * p], e[2 * p + 1]);
 }
 
-// r = x[0..K) * y mod 2^(32K)   (x is the low block of a wider array)
+// r = x[0..K) * y mod 2^(32K)   (x is the low block of a wider array; pad limb of r cleared)
 template <int K, int XN>
-DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32_t (&y)[K]) {
+DKG_HD void block_mul_lo(uint32_t (&r)[kpad<K>], const uint32_t (&x)[XN], const uint32_t (&y)[kpad<K>]) {
   static_assert(XN >= K, "x too short");
-  uint32_t E[K], O[K];
+  // E[p] = limb p as seen by the even-position chains, O[q] = limb q + 1 as seen by the odd ones; a
+  // product at position i + j <= K - 2 is a full 64-bit accumulate, at position K - 1 its low half
+  // only (it ends its chain: the carry out would leave the block)
+  uint32_t E[K + 1], O[K + 1];
 #pragma unroll
-  for (int i = 0; i < K; i++) { E[i] = 0; O[i] = 0; }
+  for (int i = 0; i < K + 1; i++) { E[i] = 0; O[i] = 0; }
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    // E chain: i = j (mod 2), limb position i+j (even) <= K-2, pair (i+j, i+j+1) always in range
     {
       const int i0 = j & 1;
-      if (i0 + j <= K - 2) {
-        mad_cc(E[i0 + j], E[i0 + j + 1], x[i0], y[j]);
 #pragma unroll
-        for (int i = i0 + 2; i + j <= K - 2; i += 2) madc_cc(E[i + j], E[i + j + 1], x[i], y[j]);
+      for (int i = i0; i + j <= K - 1; i += 2) {
+        const int pos = i + j;
+        if (pos <= K - 2) { if (i == i0) mad_cc(E[pos], E[pos + 1], x[i], y[j]); else madc_cc(E[pos], E[pos + 1], x[i], y[j]); }
+        else { if (i == i0) mad_lo(E[pos], x[i], y[j]); else madc_lo(E[pos], x[i], y[j]); }
       }
     }
-    // O chain: i != j (mod 2), limb position i+j (odd) stored at O[i+j-1]; position K-1 keeps
-    // only its low half
     {
       const int i0 = (j & 1) ^ 1;
-      if (i0 + j <= K - 3) {
-        mad_cc(O[i0 + j - 1], O[i0 + j], x[i0], y[j]);
 #pragma unroll
-        for (int i = i0 + 2; i + j <= K - 3; i += 2) madc_cc(O[i + j - 1], O[i + j], x[i], y[j]);
-        madc_lo(O[K - 2], x[K - 1 - j], y[j]);  // the element at position K-1, low half only
-      } else if (i0 + j == K - 1) {
-        mad_lo(O[K - 2], x[i0], y[j]);
+      for (int i = i0; i + j <= K - 1; i += 2) {
+        const int q = i + j - 1;
+        if (q + 1 <= K - 2) { if (i == i0) mad_cc(O[q], O[q + 1], x[i], y[j]); else madc_cc(O[q], O[q + 1], x[i], y[j]); }
+        else { if (i == i0) mad_lo(O[q], x[i], y[j]); else madc_lo(O[q], x[i], y[j]); }
       }
     }
   }
@@ -214,6 +223,7 @@ DKG_HD void block_mul_lo(uint32_t (&r)[K], const uint32_t (&x)[XN], const uint32
   for (int p = 2; p < K - 1; p++) { r[p] = E[p]; addc_cc(r[p], O[p - 1]); }
   r[K - 1] = E[K - 1];
   addc(r[K - 1], O[K - 2]);
+  if (K & 1) r[K] = 0;
 }
 
 // Pair schedule of column c of the block product scan: N*Q products, operand products, quotient
@@ -324,8 +334,13 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
 
   // position of the NEXT pair in the tabulated schedule (SCHED IO policies)
   auto sched = io.sched_begin(IO::SCHED ? sched_offset<M>(MODE) + 1 : 0);
+  // the schedule word is read ONE block product ahead: its shared-memory latency (load, move to the
+  // uniform datapath, decode) hides under the running block product instead of delaying the next
+  uint32_t sched_ahead = 0;
+  if constexpr (IO::SCHED) sched_ahead = io.sched_word(sched, 0);
 
-  uint32_t xb[K], yb[K];
+  constexpr int KP = kpad<K>;
+  uint32_t xb[KP], yb[KP];
   // operands of the very first block product (everything after it is prefetched)
   {
     const PairDesc d = Plan(0, MODE).at(0, 0);
@@ -344,7 +359,7 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
     for (int p = K + 2; p < 2 * K + 2; p++) e[p] = 0;
 
     if (MODE == MONT_REDC && c < M) {
-      uint32_t tb[K];
+      uint32_t tb[KP];
       io.load_x(c, tb);
       add_cc(e[0], tb[0]);
 #pragma unroll
@@ -356,8 +371,8 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
     if (MODE == MONT_SQR && (c & 1) == 0 && c >= 2) {
       // carry-bit correction of the doubled operand (see ColPlan): + t_{j-1} * X_j at column 2j
       const int j = c >> 1;
-      const uint32_t mask = 0u - (io.x_limb(j * K - 1) >> 31);
-      uint32_t tb[K];
+      const uint32_t mask = 0u - (io.x_top_limb(j - 1) >> 31);
+      uint32_t tb[KP];
       io.load_x(j, tb);
       add_cc(e[0], tb[0] & mask);
 #pragma unroll
@@ -392,8 +407,9 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
         // block product, its x operand loaded right after
         PairDesc nx;
         if constexpr (IO::SCHED) {
-          nx = unpack_desc(io.sched_word(sched, 0));
+          nx = unpack_desc(sched_ahead);
           sched = io.sched_next(sched);
+          sched_ahead = io.sched_word(sched, 0);   // (one word past the list's terminator at the very end: unused)
         } else {
           nx.kind = PAIR_NONE; nx.xi = 0; nx.yi = 0;
           if (t + 1 < plan.total) nx = plan.at(c, t + 1);
@@ -411,9 +427,10 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
     if (plan.total > 0) acc_merge<K>(a, e);
 
     if (c >= M) {
-      uint32_t ob[K];
+      uint32_t ob[KP];
 #pragma unroll
       for (int p = 0; p < K; p++) ob[p] = e[p];
+      if (K & 1) ob[K] = 0;
       io.store_x(c - M, ob);
     }
 #pragma unroll
@@ -425,7 +442,7 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
   const uint32_t mask = 0u - Tc[0];
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {
-    uint32_t tb[K], nb[K];
+    uint32_t tb[kpad<K>], nb[kpad<K>];
     io.load_x(b, tb);
     io.load_n(b, nb);
 #pragma unroll
@@ -443,7 +460,7 @@ template <int K, int M, class IO>
 DKG_HD uint32_t geq_n(const IO& io) {
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {
-    uint32_t xb[K], nb[K];
+    uint32_t xb[kpad<K>], nb[kpad<K>];
     io.load_x(b, xb);
     io.load_n(b, nb);
 #pragma unroll
@@ -460,7 +477,7 @@ template <int K, int M, class IO>
 DKG_HD void sub_n_masked(const IO& io, uint32_t mask) {
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {
-    uint32_t xb[K], nb[K];
+    uint32_t xb[kpad<K>], nb[kpad<K>];
     io.load_x(b, xb);
     io.load_n(b, nb);
 #pragma unroll

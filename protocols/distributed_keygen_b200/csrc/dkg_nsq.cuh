@@ -29,11 +29,14 @@ namespace dkg {
 // quotient blocks just written by the a-component's reduction (global, same vector layout),
 // N / Dneg: shared, CTA-uniform.  Whole vectors per access: conflict-free like the block loads.
 template <int K, int M>
-__device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const typename VecSel<K>::T* mq,
+__device__ __forceinline__ void pair_fixup(typename VecSel<kpad<K>>::T* Bv, const typename VecSel<kpad<K>>::T* mq,
                                            const uint32_t* Ns, const uint32_t* Dneg) {
-  using V = typename VecSel<K>::T;
-  constexpr int VW = VecSel<K>::VW;
-  constexpr int LV = K * M / VW;
+  constexpr int KP = kpad<K>;
+  using V = typename VecSel<KP>::T;
+  constexpr int VW = VecSel<KP>::VW;
+  constexpr int LV = KP * M / VW;
+  // odd K: the last limb of every slot is a pad (zero in b, N and Dneg); the carry steps over it
+  auto is_pad = [](int v, int k) -> bool { return (K & 1) && (v * VW + k) % KP == K; };
   // S = b + (R - m) = b + ~m + 1
   uint32_t carry = 1;
   for (int v = 0; v < LV; ++v) {
@@ -42,6 +45,7 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const type
     unpack(mq[(size_t)v * 32], mm);
 #pragma unroll
     for (int k = 0; k < VW; ++k) {
+      if (is_pad(v, k)) { bb[k] = 0; continue; }
       const uint64_t s = (uint64_t)bb[k] + (uint32_t)~mm[k] + carry;
       bb[k] = (uint32_t)s;
       carry = (uint32_t)(s >> 32);
@@ -59,6 +63,7 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const type
       unpack(Bv[v * 32], bb);
 #pragma unroll
       for (int k = 0; k < VW; ++k) {
+        if (is_pad(v, k)) continue;
         const uint64_t s = (uint64_t)bb[k] + (Dneg[v * VW + k] & mask) + c2;
         bb[k] = (uint32_t)s;
         c2 = (uint32_t)(s >> 32);
@@ -73,6 +78,7 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<K>::T* Bv, const type
         unpack(Bv[v * 32], bb);
 #pragma unroll
         for (int k = 0; k < VW; ++k) {
+          if (is_pad(v, k)) continue;
           const uint64_t d = (uint64_t)bb[k] - (Ns[v * VW + k] & mask2) - borrow;
           bb[k] = (uint32_t)d;
           borrow = (uint32_t)(d >> 63);
@@ -92,26 +98,28 @@ constexpr int kNsqSchedWords = sched_offset<M>(kSchedModes);
 template <int K, int M, bool BG = false>
 __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const NsqParams p) {
   static_assert(kNsqSchedWords<M> == sched_total_words_closed(M), "schedule table size: host formula out of sync with ColPlan");
-  using V = typename VecSel<K>::T;
-  constexpr int VW = VecSel<K>::VW;
-  constexpr int Lp = K * M;
+  constexpr int KP = kpad<K>;          // slot of one block in memory (odd K: one zero pad limb)
+  using V = typename VecSel<KP>::T;
+  constexpr int VW = VecSel<KP>::VW;
+  constexpr int Lp = KP * M;           // limbs of a number in memory
+  constexpr int La = K * M;            // limbs of a number in the pairs_in / pairs_out rows (R = 2^(32 La))
   constexpr int LV = Lp / VW;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // N[Lp] | NINV[K] | DNEG[Lp]
-  constexpr int UNI0 = ((2 * Lp + K) * 4 + 15) / 16 * 16;
+  uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // N[Lp] | NINV[KP] | DNEG[Lp]  (slot layout)
+  constexpr int UNI0 = ((2 * Lp + KP) * 4 + 15) / 16 * 16;
   // ... | schedule table (kNsqSchedWords<M> words, see fill_schedule)
   constexpr int UNI = UNI0 + (kNsqSchedWords<M> * 4 + 15) / 16 * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * Lp + K; i += blockDim.x) U32[i] = p.consts[i];
+  for (int i = threadIdx.x; i < 2 * Lp + KP; i += blockDim.x) U32[i] = p.consts[i];
   fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw + UNI0));
   __syncthreads();
   const uint32_t* Ns32 = U32;
-  const uint32_t* Dneg = U32 + Lp + K;
+  const uint32_t* Dneg = U32 + Lp + KP;
 
   V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * (BG ? 1 : 2) * LV * 32;
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
-  const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
+  const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + KP);
   const V* ONEA = Cg + 2 * LV, *ONEB = Cg + 3 * LV;
   // the six constants again, lane-replicated ([v][lane]) so that they can be multiplication operands
   const V* Crep = Cg + 6 * LV + lane;
@@ -165,11 +173,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
 
     // rows of 2*Lp limbs: a then b; idle lanes get the pair of 1
     for (int r = 0; r < 32; ++r) {
-      const uint32_t* row = p.pairs_in + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
-      for (int l = lane; l < Lp; l += 32) {
+      const uint32_t* row = p.pairs_in + (first + (unsigned long long)r) * (unsigned long long)(2 * La);
+      for (int l = lane; l < Lp; l += 32) {          // l: limb in slot layout, src: the dense limb (or a pad)
         const int i = ((l / VW) * 32 + r) * VW + (l % VW);
-        Aw32[i] = (r < cnt) ? row[l] : (l == 0 ? 1u : 0u);
-        Bw32[i] = (r < cnt) ? row[Lp + l] : 0u;
+        const int src = (l / KP) * K + (l % KP);
+        const bool pad = (l % KP) >= K;
+        Aw32[i] = pad ? 0u : ((r < cnt) ? row[src] : (l == 0 ? 1u : 0u));
+        Bw32[i] = (pad || r >= cnt) ? 0u : row[La + src];
       }
     }
     __syncwarp();
@@ -244,11 +254,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
     __syncwarp();
 
     for (int r = 0; r < cnt; ++r) {
-      uint32_t* row = p.pairs_out + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
+      uint32_t* row = p.pairs_out + (first + (unsigned long long)r) * (unsigned long long)(2 * La);
       for (int l = lane; l < Lp; l += 32) {
+        if ((l % KP) >= K) continue;
         const int i = ((l / VW) * 32 + r) * VW + (l % VW);
-        row[l] = Aw32[i];
-        row[Lp + l] = Bw32[i];
+        const int dst = (l / KP) * K + (l % KP);
+        row[dst] = Aw32[i];
+        row[La + dst] = Bw32[i];
       }
     }
     __syncwarp();
@@ -275,25 +287,27 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
 // window against 6 squarings + P multiplications: < 1 % of the instructions).
 template <int K, int M, bool BG = false>
 __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(const NsqMultiParams p) {
-  using V = typename VecSel<K>::T;
-  constexpr int VW = VecSel<K>::VW;
-  constexpr int Lp = K * M;
+  constexpr int KP = kpad<K>;          // slot of one block in memory (odd K: one zero pad limb)
+  using V = typename VecSel<KP>::T;
+  constexpr int VW = VecSel<KP>::VW;
+  constexpr int Lp = KP * M;           // limbs of a number in memory
+  constexpr int La = K * M;            // limbs of a number in the pairs_in / pairs_out rows (R = 2^(32 La))
   constexpr int LV = Lp / VW;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // same uniform area as modexp_nsq_kernel
-  constexpr int UNI0 = ((2 * Lp + K) * 4 + 15) / 16 * 16;
+  constexpr int UNI0 = ((2 * Lp + KP) * 4 + 15) / 16 * 16;
   constexpr int UNI = UNI0 + (kNsqSchedWords<M> * 4 + 15) / 16 * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * Lp + K; i += blockDim.x) U32[i] = p.consts[i];
+  for (int i = threadIdx.x; i < 2 * Lp + KP; i += blockDim.x) U32[i] = p.consts[i];
   fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw + UNI0));
   __syncthreads();
   const uint32_t* Ns32 = U32;
-  const uint32_t* Dneg = U32 + Lp + K;
+  const uint32_t* Dneg = U32 + Lp + KP;
 
   V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * (BG ? 1 : 2) * LV * 32;
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
-  const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + K);
+  const V* Cg = reinterpret_cast<const V*>(p.consts + 2 * Lp + KP);
   const V* Crep = Cg + 6 * LV + lane;
   const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
           *ONEBr = Crep + (size_t)3 * LV * 32,
@@ -357,11 +371,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
     const int cnt = (int)((p.count - first) < 32ull ? (p.count - first) : 32ull);
 
     for (int r = 0; r < 32; ++r) {
-      const uint32_t* row = p.pairs_in + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
-      for (int l = lane; l < Lp; l += 32) {
+      const uint32_t* row = p.pairs_in + (first + (unsigned long long)r) * (unsigned long long)(2 * La);
+      for (int l = lane; l < Lp; l += 32) {          // l: limb in slot layout, src: the dense limb (or a pad)
         const int i = ((l / VW) * 32 + r) * VW + (l % VW);
-        Aw32[i] = (r < cnt) ? row[l] : (l == 0 ? 1u : 0u);
-        Bw32[i] = (r < cnt) ? row[Lp + l] : 0u;
+        const int src = (l / KP) * K + (l % KP);
+        const bool pad = (l % KP) >= K;
+        Aw32[i] = pad ? 0u : ((r < cnt) ? row[src] : (l == 0 ? 1u : 0u));
+        Bw32[i] = (pad || r >= cnt) ? 0u : row[La + src];
       }
     }
     __syncwarp();
@@ -398,13 +414,15 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
       // (D = 2: the single bucket is the result and is already in (A, B); otherwise S is)
       pair_mul(PLAIN1r, ZEROr);   // out of the Montgomery domain
       __syncwarp();
-      uint32_t* outp = p.pairs_out + (size_t)q * p.count * (size_t)(2 * Lp);
+      uint32_t* outp = p.pairs_out + (size_t)q * p.count * (size_t)(2 * La);
       for (int r = 0; r < cnt; ++r) {
-        uint32_t* row = outp + (first + (unsigned long long)r) * (unsigned long long)(2 * Lp);
+        uint32_t* row = outp + (first + (unsigned long long)r) * (unsigned long long)(2 * La);
         for (int l = lane; l < Lp; l += 32) {
+          if ((l % KP) >= K) continue;
           const int i = ((l / VW) * 32 + r) * VW + (l % VW);
-          row[l] = Aw32[i];
-          row[Lp + l] = Bw32[i];
+          const int dst = (l / KP) * K + (l % KP);
+          row[dst] = Aw32[i];
+          row[La + dst] = Bw32[i];
         }
       }
       __syncwarp();

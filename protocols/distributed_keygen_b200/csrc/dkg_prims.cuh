@@ -43,6 +43,14 @@ DKG_HD void madc_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
   asm volatile("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmadc.lo.cc.u32 l, %1, %2, l;\n\t"
                "madc.hi.cc.u32 h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}" : "+l"(acc) : "r"(a), "r"(b));
 }
+// last element of a chain together with the count of its carry out (one statement: ptxas keeps the
+// carry add next to the chain instead of parking the carry predicates of a whole block product in a
+// mask register, which it did for odd block sizes: 66 LOP3 per block product)
+DKG_HD void madc_cc64_count(uint64_t& acc, uint32_t a, uint32_t b, uint32_t& cnt) {
+  asm volatile("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmadc.lo.cc.u32 l, %2, %3, l;\n\t"
+               "madc.hi.cc.u32 h, %2, %3, h;\n\taddc.u32 %1, %1, 0;\n\tmov.b64 %0, {l, h};\n\t}"
+               : "+l"(acc), "+r"(cnt) : "r"(a), "r"(b));
+}
 // Explicit pair <-> halves moves.  Written as (volatile) mov.b64 rather than shifts and ors: ptxas
 // then keeps the halves where the pair lives; with the C++ form it re-paired ~30 more registers
 // per block product.
@@ -99,6 +107,10 @@ DKG_HD void madc_cc64(uint64_t& acc, uint32_t a, uint32_t b) {
   uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
   madc_cc(lo, hi, a, b);
   acc = ((uint64_t)hi << 32) | lo;
+}
+DKG_HD void madc_cc64_count(uint64_t& acc, uint32_t a, uint32_t b, uint32_t& cnt) {
+  madc_cc64(acc, a, b);
+  detail::add3(cnt, 0, detail::cf(), false);
 }
 DKG_HD uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 DKG_HD void unpack64(uint64_t v, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }

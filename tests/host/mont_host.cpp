@@ -15,22 +15,27 @@ struct HostIO {
   int sched_begin(int) const { return 0; }
   int sched_next(int p) const { return p; }
   uint32_t sched_word(int, int) const { return 0; }
-  void load_s(int i, uint32_t (&r)[K]) const { std::memcpy(r, S + i * K, K * 4); }
-  void load_x(int i, uint32_t (&r)[K]) const { std::memcpy(r, X + i * K, K * 4); }
-  uint32_t x_limb(int l) const { return X[l]; }
-  void load_xs2(bool from_s, int i, uint32_t (&r)[K]) const {
+  // blocks are dense in memory (K limbs); the kernels' operand arrays are slots of KP = K + (K & 1)
+  // limbs whose pad limb is zero
+  static constexpr int KP = dkg::kpad<K>;
+  static void get(uint32_t (&r)[KP], const uint32_t* src) { std::memset(r, 0, sizeof(r)); std::memcpy(r, src, K * 4); }
+  void load_s(int i, uint32_t (&r)[KP]) const { get(r, S + i * K); }
+  void load_x(int i, uint32_t (&r)[KP]) const { get(r, X + i * K); }
+  uint32_t x_top_limb(int b) const { return X[b * K + K - 1]; }
+  void load_xs2(bool from_s, int i, uint32_t (&r)[KP]) const {
     const uint32_t* v = from_s ? S : X;
+    std::memset(r, 0, sizeof(r));
     for (int p = 0; p < K; ++p) {
       const int l = i * K + p;
       r[p] = (v[l] << 1) | (l > 0 ? v[l - 1] >> 31 : 0u);
     }
   }
-  void load_xs(bool from_s, int i, uint32_t (&r)[K]) const { std::memcpy(r, (from_s ? S : X) + i * K, K * 4); }
-  void load_y(int j, uint32_t (&r)[K]) const { std::memcpy(r, Y + j * K, K * 4); }
-  void load_q(int i, uint32_t (&r)[K]) const { std::memcpy(r, Q + i * K, K * 4); }
-  void load_n(int j, uint32_t (&r)[K]) const { std::memcpy(r, N + j * K, K * 4); }
-  void load_ninv(uint32_t (&r)[K]) const { std::memcpy(r, NI, K * 4); }
-  static constexpr int VW = (K % 4 == 0) ? 4 : 2;
+  void load_xs(bool from_s, int i, uint32_t (&r)[KP]) const { get(r, (from_s ? S : X) + i * K); }
+  void load_y(int j, uint32_t (&r)[KP]) const { get(r, Y + j * K); }
+  void load_q(int i, uint32_t (&r)[KP]) const { get(r, Q + i * K); }
+  void load_n(int j, uint32_t (&r)[KP]) const { get(r, N + j * K); }
+  void load_ninv(uint32_t (&r)[KP]) const { get(r, NI); }
+  static constexpr int VW = (KP % 4 == 0) ? 4 : 2;
   struct Prefetch { const uint32_t* base; };
   Prefetch prefetch_desc(int kind, int blk) const {
     if (kind == dkg::PAIR_XY) return Prefetch{Y + blk * K};
@@ -39,11 +44,12 @@ struct HostIO {
     if (kind == dkg::PAIR_SY2) return Prefetch{Y2 + blk * K};
     return Prefetch{nullptr};
   }
-  void prefetch_load(const Prefetch& pf, int v, uint32_t (&r)[K]) const {
-    if (pf.base) std::memcpy(r + v * VW, pf.base + v * VW, VW * 4);
+  void prefetch_load(const Prefetch& pf, int v, uint32_t (&r)[KP]) const {
+    if (!pf.base) return;
+    for (int e = v * VW; e < v * VW + VW; ++e) r[e] = e < K ? pf.base[e] : 0u;
   }
-  void store_q(int i, const uint32_t (&r)[K]) const { std::memcpy(Q + i * K, r, K * 4); }
-  void store_x(int i, const uint32_t (&r)[K]) const { std::memcpy(X + i * K, r, K * 4); }
+  void store_q(int i, const uint32_t (&r)[KP]) const { std::memcpy(Q + i * K, r, K * 4); }
+  void store_x(int i, const uint32_t (&r)[KP]) const { std::memcpy(X + i * K, r, K * 4); }
 };
 
 template <int K, int M>
@@ -71,7 +77,7 @@ int run(int mode, uint32_t* x, const uint32_t* y, const uint32_t* n, const uint3
 extern "C" int host_mont2(int K, int M, int mode, uint32_t* x, const uint32_t* y, const uint32_t* n,
                           const uint32_t* ninv, int canon, const uint32_t* s_op, const uint32_t* y2) {
   CASE(4, 1) CASE(4, 3) CASE(4, 2) CASE(4, 5) CASE(6, 3) CASE(8, 4) CASE(12, 3) CASE(16, 2)
-  CASE(16, 8) CASE(12, 11) CASE(22, 3) CASE(22, 6) CASE(16, 16) CASE(14, 5) CASE(12, 6)
+  CASE(16, 8) CASE(12, 11) CASE(22, 3) CASE(22, 6) CASE(16, 16) CASE(14, 5) CASE(12, 6) CASE(14, 7) CASE(13, 5) CASE(13, 10) CASE(5, 3) CASE(7, 2) CASE(9, 1)
   return -1;
 }
 

@@ -112,7 +112,7 @@ def test_full_wave_plus_ragged_tail_against_gmp(dealer_vectors):
     e = exps[pid]
     ctx = eng.ModexpContext(dk.n * dk.n, e, root=dk.n)
     info = ctx.info()
-    assert info["pair_arithmetic"] == 1 and (info["pair_K"], info["pair_M"]) == (14, 5)
+    assert info["pair_arithmetic"] == 1 and (info["pair_K"], info["pair_M"]) == (13, 5)
     wave = info["ctas"] * info["warps_per_cta"] * 32
     count = wave + 17
     L = ctx.limbs

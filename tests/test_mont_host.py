@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "protocols", "distributed_keygen_b200", "csrc")
 
 SHAPES = [(4, 1), (4, 3), (4, 2), (4, 5), (6, 3), (8, 4), (12, 3), (16, 2), (16, 8), (12, 11),
-          (22, 3), (22, 6), (16, 16), (14, 5), (12, 6)]
+          (22, 3), (22, 6), (16, 16), (14, 5), (12, 6), (14, 7),
+          (13, 5), (13, 10), (5, 3), (7, 2), (9, 1)]   # odd block sizes: slots of K + 1 limbs on the device
 
 
 @pytest.fixture(scope="module")
@@ -97,7 +98,7 @@ def test_mont_exponentiation_chain_host(lib):
     assert _call(lib, K, M, 2, acc, 0, n, ninv, 1) == pow(base, e, n)
 
 
-@pytest.mark.parametrize("K,M", [(4, 2), (12, 6), (14, 5), (16, 4) if False else (16, 2), (22, 3)])
+@pytest.mark.parametrize("K,M", [(4, 2), (12, 6), (14, 5), (16, 2), (22, 3), (13, 5), (13, 10), (5, 3), (14, 7)])
 def test_pair_modes_host(lib, K, M):
     """MONT_MUL2S (x <- 2xy/R) and MONT_MULADD (x <- (xy + s y2)/R) used by the mod N^2 pair
     arithmetic, with operands up to R and a modulus with >= 3 spare bits."""

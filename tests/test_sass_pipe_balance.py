@@ -2,7 +2,7 @@
 function whether register moves and carry adds go to the ALU pipe (MOV, IADD3.X) or to the multiplier
 pipe (IMAD.MOV.U32, IMAD.X) -- the one pipe the exponentiation saturates.  A compiler change that
 undoes the ballast's effect would silently cost ~5-15 % throughput; this test fails loudly instead.
-Checked on the SASS of the headline kernels, modexp_nsq_kernel<14,5> and modexp_nsq_multi_kernel<14,5>,
+Checked on the SASS of the headline kernels, modexp_nsq_kernel and modexp_nsq_multi_kernel at the shapes of 2048-bit-class keys, <13,5> and <14,5>,
 inside their noinline Montgomery product (the target of their CALLs)."""
 from __future__ import annotations
 
@@ -13,12 +13,14 @@ import subprocess
 
 import pytest
 
-KERNELS = ["_ZN3dkg17modexp_nsq_kernelILi14ELi5ELb0EEEvNS_9NsqParamsE",
-           "_ZN3dkg23modexp_nsq_multi_kernelILi14ELi5ELb0EEEvNS_14NsqMultiParamsE"]
+KERNELS = [("_ZN3dkg17modexp_nsq_kernelILi13ELi5ELb0EEEvNS_9NsqParamsE", 13),
+           ("_ZN3dkg23modexp_nsq_multi_kernelILi13ELi5ELb0EEEvNS_14NsqMultiParamsE", 13),
+           ("_ZN3dkg17modexp_nsq_kernelILi14ELi5ELb0EEEvNS_9NsqParamsE", 14),
+           ("_ZN3dkg23modexp_nsq_multi_kernelILi14ELi5ELb0EEEvNS_14NsqMultiParamsE", 14)]
 
 
-@pytest.mark.parametrize("KERNEL", KERNELS)
-def test_hot_montgomery_product_keeps_the_multiplier_pipe_for_multiplies(KERNEL):
+@pytest.mark.parametrize("KERNEL,K", KERNELS)
+def test_hot_montgomery_product_keeps_the_multiplier_pipe_for_multiplies(KERNEL, K):
     from protocols.distributed_keygen_b200 import _native
 
     if shutil.which("cuobjdump") is None:
@@ -34,7 +36,7 @@ def test_hot_montgomery_product_keeps_the_multiplier_pipe_for_multiplies(KERNEL)
     wide = sum(v for k, v in count.items() if k == "IMAD.WIDE")
     moves = count.get("IMAD.MOV", 0)
     carry_adds = count.get("IMAD.X", 0)
-    assert wide >= 14 * 14, f"expected the unrolled 14x14 block product, found {wide} IMAD.WIDE"
+    assert wide >= K * K, f"expected the unrolled {K}x{K} block product, found {wide} IMAD.WIDE"
     assert moves == 0, f"{moves} IMAD.MOV on the multiplier pipe inside the hot function: the pipe ballast no longer works"
     assert carry_adds <= 16, f"{carry_adds} IMAD.X on the multiplier pipe inside the hot function (was 12)"
     # the ballast itself must still be there (never executed, it only tips ptxas's static balance)
