@@ -1320,7 +1320,7 @@ namespace {
 struct GroupedPlan {
   Shape shape{};
   dkg::GroupedFn kernel = nullptr;
-  int Lp = 0, K = 0, wbits = 1, ndigits = 1, warps = 1, ctas = 1;
+  int Lp = 0, K = 0, Ka = 0, wbits = 1, ndigits = 1, warps = 1, ctas = 1;   // K, Lp: slot layout; Ka: arithmetic block
   size_t smem = 0, q_off = 0, scratch_per_warp = 0;
 };
 
@@ -1333,7 +1333,7 @@ int plan_grouped(DeviceState* d, int limbs, int ebits, size_t count, GroupedPlan
   // 304 k vs 222 k modexps/s on 65-limb candidates
   static constexpr Shape kGroupedPref[] = {
       {4, 1}, {4, 2}, {4, 3}, {8, 2}, {6, 3}, {12, 2}, {16, 2}, {12, 3}, {16, 3}, {16, 4},
-      {14, 5}, {22, 3}, {16, 5}, {16, 6}, {16, 8}, {12, 11},
+      {13, 5}, {14, 5}, {22, 3}, {16, 5}, {16, 6}, {16, 8}, {12, 11},
   };
   if (!plan->kernel)
     for (const Shape& sh : kGroupedPref)
@@ -1342,8 +1342,9 @@ int plan_grouped(DeviceState* d, int limbs, int ebits, size_t count, GroupedPlan
     for (const Shape& sh : kShapes)
       if (sh.K * sh.M >= limbs && (plan->kernel = lookup_grouped(sh.K, sh.M)) != nullptr) { plan->shape = sh; break; }
   if (!plan->kernel) return fail(DKG_ERR_UNSUPPORTED, "modulus wider than the grouped kernel shapes (132 limbs)");
-  plan->Lp = plan->shape.K * plan->shape.M;
-  plan->K = plan->shape.K;
+  plan->Ka = plan->shape.K;
+  plan->K = plan->shape.K + (plan->shape.K & 1);
+  plan->Lp = plan->K * plan->shape.M;
   plan->wbits = choose_window(ebits);
   plan->ndigits = std::max(1, (ebits + plan->wbits - 1) / plan->wbits);
   const size_t per_warp_smem = ((size_t)2 * plan->Lp + plan->K) * 32 * 4;
@@ -1412,7 +1413,7 @@ int launch_grouped(DeviceState* d, const GroupedPlan& plan, const uint32_t* d_mo
   CUDA_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), d->stream));
   dkg::GroupedParams p{};
   p.moduli = d_mod; p.exps = d_exp; p.bases = d_bases; p.out = d_out; p.groups = groups;
-  p.per_group = per_group; p.limbs = limbs; p.exp_limbs = exp_limbs; p.K = plan.K; p.Lp = plan.Lp;
+  p.per_group = per_group; p.limbs = limbs; p.exp_limbs = exp_limbs; p.K = plan.K; p.Lp = plan.Lp; p.Ka = plan.Ka;
   p.wbits = plan.wbits; p.ndigits = plan.ndigits; p.gconsts = d_gc; p.digits = d_dig; p.scratch = d->scratch;
   p.scratch_per_warp = plan.scratch_per_warp; p.scratch_q_offset = plan.q_off; p.counter = d->counter;
   dkg::launch_group_setup(p, d->stream);

@@ -19,12 +19,15 @@ namespace dkg {
 static __global__ void __launch_bounds__(64) group_setup_kernel(const GroupedParams p) {
   const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= p.groups) return;
-  const int Lp = p.Lp, K = p.K;
+  // arithmetic: blocks of K limbs, Lp limbs per number, R = 2^(32 Lp); memory: slots of KP limbs
+  const int KP = p.K, K = p.Ka, Lp = K * (p.Lp / KP);
+  auto slot = [&](int l) { return (l / K) * KP + l % K; };
   uint32_t n[kGroupedMaxLimbs], x[kGroupedMaxLimbs], d[kGroupedMaxLimbs];
   const uint32_t* src = p.moduli + g * (unsigned long long)p.limbs;
   for (int l = 0; l < Lp; ++l) { n[l] = l < p.limbs ? src[l] : 0u; x[l] = 0; }
-  uint32_t* row = p.gconsts + g * (unsigned long long)(3 * Lp + K);
-  for (int l = 0; l < Lp; ++l) row[l] = n[l];
+  uint32_t* row = p.gconsts + g * (unsigned long long)(3 * p.Lp + KP);
+  for (int l = 0; l < 3 * p.Lp + KP; ++l) row[l] = 0;
+  for (int l = 0; l < Lp; ++l) row[slot(l)] = n[l];
 
   // -N^-1 mod 2^(32K) by Hensel lifting one limb at a time (prod = n * inv mod 2^(32K))
   {
@@ -46,7 +49,7 @@ static __global__ void __launch_bounds__(64) group_setup_kernel(const GroupedPar
     uint64_t carry = 1;
     for (int i = 0; i < K; ++i) {
       const uint64_t t = (uint64_t)(~inv[i]) + carry;
-      row[Lp + i] = (uint32_t)t;
+      row[p.Lp + i] = (uint32_t)t;
       carry = t >> 32;
     }
   }
@@ -72,9 +75,9 @@ static __global__ void __launch_bounds__(64) group_setup_kernel(const GroupedPar
     if (take)
       for (int l = 0; l < Lp; ++l) x[l] = d[l];
     if (k == 32 * Lp - 1)
-      for (int l = 0; l < Lp; ++l) row[Lp + K + Lp + l] = x[l];  // ONER
+      for (int l = 0; l < Lp; ++l) row[p.Lp + KP + p.Lp + slot(l)] = x[l];  // ONER
   }
-  for (int l = 0; l < Lp; ++l) row[Lp + K + l] = x[l];  // R2
+  for (int l = 0; l < Lp; ++l) row[p.Lp + KP + slot(l)] = x[l];  // R2
 
   // window digits, most significant first, padded with leading zeros to p.ndigits windows
   const uint32_t* e = p.exps + g * (unsigned long long)p.exp_limbs;
@@ -92,11 +95,12 @@ static __global__ void __launch_bounds__(64) group_setup_kernel(const GroupedPar
 
 template <int K, int M>
 __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(const GroupedParams p) {
-  using V = typename VecSel<K>::T;
-  constexpr int VW = VecSel<K>::VW;
-  constexpr int Lp = K * M;
+  constexpr int KP = kpad<K>;          // slot of one block in memory (odd K: one zero pad limb)
+  using V = typename VecSel<KP>::T;
+  constexpr int VW = VecSel<KP>::VW;
+  constexpr int Lp = KP * M;           // limbs of a number in memory
   constexpr int LV = Lp / VW;
-  constexpr int KV = K / VW;
+  constexpr int KV = KP / VW;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -139,20 +143,22 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
 
     for (int r = 0; r < 32; ++r) {
       const uint32_t* row = p.bases + (first + (unsigned long long)r) * (unsigned long long)p.limbs;
-      for (int l = lane; l < Lp; l += 32) {
-        uint32_t v = (r < cnt) ? (l < p.limbs ? row[l] : 0u) : (l == 0 ? 1u : 0u);
+      for (int l = lane; l < Lp; l += 32) {      // l: limb in slot layout, src: the dense limb (or a pad)
+        const int src = (l / KP) * K + (l % KP);
+        const bool pad = (l % KP) >= K;
+        uint32_t v = pad ? 0u : ((r < cnt) ? (src < p.limbs ? row[src] : 0u) : (l == 0 ? 1u : 0u));
         Xw32[((l / VW) * 32 + r) * VW + (l % VW)] = v;
       }
     }
     // this lane's constants
     {
-      const uint32_t* row = p.gconsts + gid * (unsigned long long)(3 * Lp + K);
+      const uint32_t* row = p.gconsts + gid * (unsigned long long)(3 * Lp + KP);
       const V* nsrc = reinterpret_cast<const V*>(row);            // rows are 8/16-byte aligned: Lp, K multiples of VW
       for (int v = 0; v < LV; ++v) Nw[v * 32 + lane] = nsrc[v];
       const V* isrc = reinterpret_cast<const V*>(row + Lp);
       for (int v = 0; v < KV; ++v) NIw[v * 32 + lane] = isrc[v];
-      const V* r2 = reinterpret_cast<const V*>(row + Lp + K);
-      const V* one = reinterpret_cast<const V*>(row + Lp + K + Lp);
+      const V* r2 = reinterpret_cast<const V*>(row + Lp + KP);
+      const V* one = reinterpret_cast<const V*>(row + Lp + KP + Lp);
       for (int v = 0; v < LV; ++v) { R2l[(size_t)v * 32 + lane] = r2[v]; ONEl[(size_t)v * 32 + lane] = one[v]; }
     }
     __syncwarp();
@@ -184,7 +190,10 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
 
     for (int r = 0; r < cnt; ++r) {
       uint32_t* row = p.out + (first + (unsigned long long)r) * (unsigned long long)p.limbs;
-      for (int l = lane; l < p.limbs; l += 32) row[l] = Xw32[((l / VW) * 32 + r) * VW + (l % VW)];
+      for (int l = lane; l < Lp; l += 32) {
+        const int dst = (l / KP) * K + (l % KP);
+        if ((l % KP) < K && dst < p.limbs) row[dst] = Xw32[((l / VW) * 32 + r) * VW + (l % VW)];
+      }
     }
     __syncwarp();
   }

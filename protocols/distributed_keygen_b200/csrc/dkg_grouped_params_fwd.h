@@ -13,9 +13,10 @@ struct GroupedParams {
   uint32_t* out;            // same shape as bases
   unsigned long long groups;
   int per_group, limbs, exp_limbs;
-  int K, Lp;
+  int K, Lp;                // memory layout: slot of one block (even), limbs of a number = K * blocks
+  int Ka;                   // arithmetic block size (Ka = K, or K - 1 with a zero pad limb per slot): R = 2^(32 Ka blocks)
   int wbits, ndigits;
-  uint32_t* gconsts;        // [groups][Lp + K + Lp + Lp]: N | NINV | R2 | ONER
+  uint32_t* gconsts;        // [groups][Lp + K + Lp + Lp]: N | NINV | R2 | ONER  (slot layout)
   uint8_t* digits;          // [groups][ndigits], most significant first
   uint32_t* scratch;
   unsigned long long scratch_per_warp, scratch_q_offset;

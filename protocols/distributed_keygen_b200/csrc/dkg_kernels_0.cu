@@ -1,7 +1,7 @@
 // Kernel instantiations, group 0 (split across translation units so they compile in parallel).
 #define DKG_GROUP 0
 #define DKG_GROUP_SHAPES(X) X(16,8) X(4,1) X(4,2) X(4,3) X(8,2)
-#define DKG_GROUP_GROUPED_SHAPES(X) X(16,8) X(4,1) X(4,2) X(4,3) X(8,2)
+#define DKG_GROUP_GROUPED_SHAPES(X) X(16,8) X(4,1) X(4,2) X(4,3) X(8,2) X(13,5)
 #define DKG_GROUP_NSQ_SHAPES(X) X(4,1) X(4,2) X(4,3) X(8,2) X(13,5)
 #include "dkg_kernels.inc"
 
