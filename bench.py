@@ -802,7 +802,7 @@ def main() -> None:
         tctx.close()
         if rank == 0:
             # the same through Python ints (the reference-shaped signatures: lists of int in and out)
-            k_int = min(B, 16384)
+            k_int = min(B, info["ctas"] * info["warps_per_cta"] * 32)   # one full wave of ciphertexts
             ints = limbs_to_ints(host_cts[:k_int])
             t0 = time.perf_counter()
             got_int = dkgmod.decrypt_sequence_local(keys, ints)
