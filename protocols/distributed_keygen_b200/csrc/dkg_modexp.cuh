@@ -138,6 +138,8 @@ struct WarpIO : XgField<typename VecSel<kpad<K>>::T, XG_> {
   // never true (a shared-space address is far below 2^32 - 1), but not provably so: guards the
   // pipe-balance ballast in mont_mul
   __device__ __forceinline__ bool never() const { return ns == 0xffffffffu; }
+  // does any lane of the warp hold a non-zero v?  (all 32 lanes call the Montgomery product together)
+  __device__ __forceinline__ bool any_lane(uint32_t v) const { return __any_sync(0xffffffffu, v != 0u); }
   __device__ __forceinline__ void load_x(int i, uint32_t (&r)[KP]) const {
     if (x_global()) {
 #pragma unroll

@@ -438,7 +438,10 @@ DKG_HD void mont_mul(const IO& io, const int MODE) {
   }
 
   if (io.never()) Tc[0] = pipe_ballast(Tc[0], Tc[1]);
-  // result = Tc[0]*R + X < R + N: subtract N once iff the carry limb is set
+  // result = Tc[0]*R + X < R + N: subtract N once iff the carry limb is set.  Skipped when no lane of
+  // the warp has it set -- always in the pair arithmetic, whose products stay below 5N <= R
+  //  -- instead of a masked pass over X and N.
+  if (!io.any_lane(Tc[0])) return;
   const uint32_t mask = 0u - Tc[0];
   uint32_t borrow = 0;
   for (int b = 0; b < M; ++b) {

@@ -11,6 +11,7 @@ struct HostIO {
   uint32_t* X; const uint32_t* Y; uint32_t* Q; const uint32_t* N; const uint32_t* NI;
   const uint32_t* S = nullptr; const uint32_t* Y2 = nullptr;
   bool never() const { return false; }
+  bool any_lane(uint32_t v) const { return v != 0; }
   static constexpr bool SCHED = false;   // the host harness recomputes the schedule from ColPlan
   int sched_begin(int) const { return 0; }
   int sched_next(int p) const { return p; }
