@@ -169,6 +169,11 @@ int dkg_threshold_decrypt_batch(dkg_threshold_ctx* ctx, const uint32_t* cipherte
 int dkg_threshold_decrypt_batch_device(dkg_threshold_ctx* ctx, const uint32_t* d_ciphertexts,
                                        uint32_t* d_plaintexts, uint32_t* d_partials,
                                        uint8_t* d_status, size_t count, void* stream);
+/* every party's partial decryptions of the same ciphertexts, no combination (loop 1 of
+ * _decrypt_sequence_raw, :463-466, for all in-process parties at once; they share one squaring
+ * chain like the call above): partials [shares][count][n2_limbs], status [shares][count] or NULL */
+int dkg_threshold_partials_batch(dkg_threshold_ctx* ctx, const uint32_t* ciphertexts, uint32_t* partials,
+                                 uint8_t* status, size_t count);
 /* one party's partial decryptions (what a distributed party computes for its broadcast) */
 int dkg_threshold_partial_decrypt_batch(dkg_threshold_ctx* ctx, int party, const uint32_t* ciphertexts,
                                         uint32_t* out, uint8_t* status, size_t count);

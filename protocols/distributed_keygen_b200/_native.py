@@ -34,7 +34,7 @@ EXPORTS = [
     "dkg_combine_ctx_create", "dkg_combine_ctx_destroy", "dkg_combine_n2_limbs",
     "dkg_combine_batch", "dkg_combine_batch_device",
     "dkg_threshold_ctx_create", "dkg_threshold_ctx_destroy", "dkg_threshold_info", "dkg_threshold_info_ex", "dkg_threshold_decrypt_batch",
-    "dkg_threshold_decrypt_batch_device",
+    "dkg_threshold_decrypt_batch_device", "dkg_threshold_partials_batch",
     "dkg_threshold_partial_decrypt_batch", "dkg_threshold_combine_batch", "dkg_host_register", "dkg_host_unregister",
     "dkg_encrypt_batch", "dkg_modexp_grouped",
     "dkg_biprime_v_batch", "dkg_jacobi_batch", "dkg_small_prime_sieve", "dkg_biprime_verdict",
@@ -85,6 +85,7 @@ def _load() -> ctypes.CDLL:
     lib.dkg_kernel_times.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double * 4096), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.dkg_threshold_info_ex.argtypes = [c_void, ctypes.POINTER(ctypes.c_int * 8)]
     lib.dkg_threshold_decrypt_batch_device.argtypes = [c_void, c_void, c_void, c_void, c_void, ctypes.c_size_t, c_void]
+    lib.dkg_threshold_partials_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_threshold_partial_decrypt_batch.argtypes = [c_void, ctypes.c_int, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_threshold_combine_batch.argtypes = [c_void, c_u32p, c_u32p, c_u8p, ctypes.c_size_t]
     lib.dkg_host_register.argtypes = [c_void, ctypes.c_size_t]

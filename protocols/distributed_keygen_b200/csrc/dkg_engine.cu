@@ -1755,7 +1755,8 @@ int launch_threshold_multi(dkg_threshold_ctx::Dev& dv, int S, const uint32_t* d_
 
 // what one device does with its shard, chunk by chunk, alternating between its two streams so the
 // copies of one chunk overlap the kernels of the other.  mode 0: decrypt (partials optional),
-// 1: one party's partial decryption, 2: combination of given partials.
+// 1: one party's partial decryption, 2: combination of given partials, 3: every party's partial
+// decryptions without the combination (status per party, [shares][count]).
 struct ThresholdJob {
   int mode = 0, party = 0;
   const uint32_t* in = nullptr;        // mode 0/1: ciphertexts [count][l2]; mode 2: partials [shares][count][l2]
@@ -1783,7 +1784,7 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
     cudaStream_t s = dv.streams[b];
     if (job.mode != 2) TRY_CUDA(cudaMallocAsync(&buf[b].in, rows_max * row_b, s));
     TRY_CUDA(cudaMallocAsync(&buf[b].part, rows_max * row_b * (need_part ? S : 1), s));
-    if (job.mode != 1) TRY_CUDA(cudaMallocAsync(&buf[b].out, rows_max * plain_b, s));
+    if (job.mode != 1 && job.mode != 3) TRY_CUDA(cudaMallocAsync(&buf[b].out, rows_max * plain_b, s));
     TRY_CUDA(cudaMallocAsync(&buf[b].st, rows_max * (size_t)(S + 1), s));
     buf[b].host_st.resize(rows_max * (size_t)(S + 1));
   }
@@ -1794,6 +1795,10 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
     if (job.status) {
       for (size_t i = 0; i < B.rows; ++i) {
         uint8_t st = 0;
+        if (job.mode == 3) {
+          for (int p = 0; p < S; ++p) job.status[(size_t)p * job.count + B.lo + i] = B.host_st[(size_t)p * B.rows + i];
+          continue;
+        }
         if (job.mode == 1) st = B.host_st[i];
         else {
           if (job.mode == 0)
@@ -1824,7 +1829,7 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
       if (job.mode == 1) {
         rc = launch_modexp(dv.parties[job.party], B.in, B.part, B.st, nullptr, rows, s);
       } else {
-        if (job.mode == 0) {
+        if (job.mode == 0 || job.mode == 3) {
           // a few ciphertexts: every party's exponentiation in ONE cooperative launch (one warp per
           // (party, ciphertext)); otherwise one wave launch per party
           bool fused = S <= dkg::kCoopMaxParties;
@@ -1840,7 +1845,7 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
               rc = launch_modexp(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, nullptr, rows, s);
           }
         }
-        if (rc == DKG_OK) rc = launch_combine(dv.combine, B.part, B.out, B.st + (size_t)S * rows, rows, s);
+        if (rc == DKG_OK && job.mode != 3) rc = launch_combine(dv.combine, B.part, B.out, B.st + (size_t)S * rows, rows, s);
       }
       if (rc != DKG_OK) { *err = g_err; break; }
     }
@@ -1848,8 +1853,8 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
       TRY_CUDA(cudaMemcpyAsync(job.partials + lo * l2, B.part, rows * row_b, cudaMemcpyDeviceToHost, s));
       if (job.status) TRY_CUDA(cudaMemcpyAsync(B.host_st.data(), B.st, rows, cudaMemcpyDeviceToHost, s));
     } else {
-      TRY_CUDA(cudaMemcpyAsync(job.plain + lo * ln, B.out, rows * plain_b, cudaMemcpyDeviceToHost, s));
-      if (job.mode == 0 && job.partials)
+      if (job.mode != 3) TRY_CUDA(cudaMemcpyAsync(job.plain + lo * ln, B.out, rows * plain_b, cudaMemcpyDeviceToHost, s));
+      if ((job.mode == 0 || job.mode == 3) && job.partials)
         for (int p = 0; p < S; ++p)
           TRY_CUDA(cudaMemcpyAsync(job.partials + ((size_t)p * job.count + lo) * l2, B.part + (size_t)p * rows * l2, rows * row_b, cudaMemcpyDeviceToHost, s));
       if (job.status) TRY_CUDA(cudaMemcpyAsync(B.host_st.data(), B.st, rows * (size_t)(S + 1), cudaMemcpyDeviceToHost, s));
@@ -2045,6 +2050,13 @@ int dkg_threshold_partial_decrypt_batch(dkg_threshold_ctx* t, int party, const u
   if (!t || party < 0 || party >= t->shares || (count && (!ciphertexts || !out))) return fail(DKG_ERR_INVALID, "bad argument");
   ThresholdJob job;
   job.mode = 1; job.party = party; job.in = ciphertexts; job.partials = out; job.status = status; job.count = count;
+  return run_threshold(t, job);
+}
+
+int dkg_threshold_partials_batch(dkg_threshold_ctx* t, const uint32_t* ciphertexts, uint32_t* partials, uint8_t* status, size_t count) {
+  if (!t || (count && (!ciphertexts || !partials))) return fail(DKG_ERR_INVALID, "null argument");
+  ThresholdJob job;
+  job.mode = 3; job.in = ciphertexts; job.partials = partials; job.status = status; job.count = count;
   return run_threshold(t, job);
 }
 

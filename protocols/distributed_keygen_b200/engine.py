@@ -404,6 +404,18 @@ class ThresholdContext:
             status.ctypes.data, count))
         return plain, status, parts
 
+    def partials_limbs(self, ciphertexts: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        """Every party's partial decryptions of the same ciphertexts in one call (one shared squaring
+        chain on the device): [count, n2_limbs] -> (partials [shares, count, n2_limbs], status
+        [shares, count])."""
+        cts = self._rows(ciphertexts, self.n2_limbs)
+        count = cts.shape[0]
+        parts = np.zeros((self.shares, count, self.n2_limbs), dtype=np.uint32)
+        status = np.zeros((self.shares, count), dtype=np.uint8)
+        _native.check(_native.lib.dkg_threshold_partials_batch(
+            self._h, cts.ctypes.data, parts.ctypes.data, status.ctypes.data, count))
+        return parts, status
+
     def partial_decrypt_limbs(self, party: int, ciphertexts: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
         cts = self._rows(ciphertexts, self.n2_limbs)
         count = cts.shape[0]

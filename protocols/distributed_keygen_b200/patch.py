@@ -27,13 +27,23 @@ What ``install()`` rebinds (reference file:line -> what runs instead):
 * new ``DistributedPaillier._b200_biprime_v_batch``: all candidates of a ``compute_modulus`` round
   (the list comprehension at ``:1313-1329``) in one call, for maintainers who edit that line.
 
+In-process parties (``distributed=False``, the reference's tests and benchmark,
+``distributed_keygen.py:203-226``): every party's coroutine calls ``partial_decrypt_batch`` on the SAME
+ciphertexts.  When the keys of all parties 1..degree+1 of a modulus are live in this process and the
+batch is large, the first such call computes every party's partial decryptions in one engine call
+(one shared chain of squarings on the device) and the other parties' calls
+pick theirs up; each party still gets exactly the values its own call would return.
+``DKG_B200_SHARE=0`` turns this off, ``DKG_B200_SHARE_MIN`` sets the smallest batch (default 4096).
+
 ``uninstall()`` restores every attribute.  Nothing here computes on the host: without the CUDA
 library / a device the patched methods raise (there is no CPU fallback).
 """
 from __future__ import annotations
 
+import hashlib
 import importlib
 import os
+import weakref
 from typing import Any, Iterable, Mapping, Sequence
 
 from . import distributed_keygen as _dk
@@ -42,6 +52,8 @@ from .paillier_shared_key import PaillierSharedKey as _GpuKey
 
 _ORIGINALS: list[tuple[Any, str, Any, bool]] = []   # (owner, attribute, old value, existed)
 _DEVICE = 0
+_PEERS: dict[int, dict[int, Any]] = {}               # n -> {player_id: weak reference to the reference key}
+_SHARED: dict[tuple[int, bytes], dict[str, Any]] = {}   # (n, digest of the batch) -> partials of all parties
 
 
 def _ref_modules(ref_pkg: Any = None) -> tuple[Any, Any, Any]:
@@ -69,6 +81,42 @@ def gpu_key(ref_key: Any) -> _GpuKey:
     return twin
 
 
+def _shared_partials(ref_key: Any, values: Sequence[int]) -> list[int] | None:
+    """This party's partial decryptions out of ONE engine call for all in-process parties of the key,
+    or None when that does not apply (see the module docstring)."""
+    from .limbs import ints_to_limbs, limbs_to_ints
+
+    if os.environ.get("DKG_B200_SHARE", "1") == "0" or not (
+            int(os.environ.get("DKG_B200_SHARE_MIN", "4096")) <= len(values) <= (1 << 21)):
+        return None
+    twin = gpu_key(ref_key)
+    n = twin.n
+    _PEERS.setdefault(n, {})[twin.player_id] = weakref.ref(ref_key)
+    need = range(1, twin.share.degree + 2)
+    live = {i: r() for i, r in _PEERS[n].items()}
+    if twin.player_id not in need or any(live.get(i) is None for i in need):
+        return None
+    twins = {i: gpu_key(live[i]) for i in need}
+    if any(k.t != twin.t or k.theta != twin.theta or k.share.degree != twin.share.degree for k in twins.values()):
+        return None
+    ctx = _dk._cached_threshold_context(twins, (_DEVICE,))
+    rows = ints_to_limbs([v % twin.n_square for v in values], ctx.n2_limbs)
+    ident = (n, hashlib.blake2b(rows.tobytes(), digest_size=16).digest())
+    entry = _SHARED.get(ident)
+    if entry is None or twin.player_id not in entry["left"]:
+        parts, status = ctx.partials_limbs(rows)
+        while len(_SHARED) >= 2:
+            _SHARED.pop(next(iter(_SHARED)))
+        entry = _SHARED[ident] = {"parts": parts, "status": status, "left": set(need)}
+    entry["left"].discard(twin.player_id)
+    mine, status = entry["parts"][twin.player_id - 1], entry["status"][twin.player_id - 1]
+    if not entry["left"]:
+        _SHARED.pop(ident, None)
+    if status.any():
+        raise ZeroDivisionError("base is not invertible for the given modulus")
+    return limbs_to_ints(mine)
+
+
 def _set(owner: Any, attr: str, value: Any) -> None:
     existed = attr in owner.__dict__
     _ORIGINALS.append((owner, attr, owner.__dict__.get(attr), existed))
@@ -80,6 +128,8 @@ def installed() -> bool:
 
 
 def uninstall() -> None:
+    _PEERS.clear()
+    _SHARED.clear()
     while _ORIGINALS:
         owner, attr, old, existed = _ORIGINALS.pop()
         if existed:
@@ -109,7 +159,9 @@ def install(ref_pkg: Any = None, device: int = 0, batched_sequence: bool = True)
         return int(ciphertext.get_value())
 
     def partial_decrypt_batch(self: Any, ciphertexts: Iterable[Any]) -> list[int]:
-        return gpu_key(self).partial_decrypt_batch([checked_value(self, c) for c in ciphertexts])
+        values = [checked_value(self, c) for c in ciphertexts]
+        shared = _shared_partials(self, values)
+        return shared if shared is not None else gpu_key(self).partial_decrypt_batch(values)
 
     def partial_decrypt(self: Any, ciphertext: Any) -> int:
         return partial_decrypt_batch(self, [ciphertext])[0]

@@ -185,6 +185,54 @@ def test_reference_sequence_on_gpu_with_encrypt_context(fixture_vectors):
     assert all(r is None for r in res[1:])
 
 
+@needs_ref
+@pytest.mark.gpu
+def test_in_process_parties_share_one_engine_call(fixture_vectors, monkeypatch):
+    """The reference's in-process parties decrypt the same sequence: once all of them are known to the
+    patch, ONE engine call (shared squaring chain) serves every party's ``partial_decrypt_batch`` --
+    with exactly the partials each party's own call returns (``DKG_B200_SHARE=0``)."""
+    from protocols.distributed_keygen_b200 import EncryptContext, engine, patch
+
+    t, parties, keys = _sets(fixture_vectors)[0]
+    n = _h(keys[0]["n"])
+    rng = random.Random(11)
+    count = 1200
+    ms = [rng.randrange(0, 1000) for _ in range(count)]
+    enc = EncryptContext(n)
+    raws = enc.encrypt([m % n for m in ms], [rng.randrange(1, n) for _ in ms])
+    enc.close()
+    monkeypatch.setenv("DKG_B200_SHARE_MIN", "1000")
+    calls = []
+    real = engine.ThresholdContext.partials_limbs
+    monkeypatch.setattr(engine.ThresholdContext, "partials_limbs", lambda self, rows: (calls.append(len(rows)), real(self, rows))[1])
+
+    def run_once(share: str):
+        monkeypatch.setenv("DKG_B200_SHARE", share)
+        patch.install(REF)
+        try:
+            schemes = rh.make_schemes(REF, keys, t)
+            ps = sorted(schemes)
+            out = []
+            for _ in range(2):          # the first pass makes every party's key known, the second shares
+                cts = {p: [rh.ciphertext(schemes[p], c) for c in raws] for p in ps}
+                partials = {p: schemes[p].secret_key.partial_decrypt_batch(cts[p]) for p in ps}
+                cts = {p: [rh.ciphertext(schemes[p], c) for c in raws] for p in ps}
+                res = rh.run([schemes[p].decrypt_sequence(cts[p], apply_encoding=False) for p in ps])
+                out.append((partials, [[int(v) for v in r] for r in res]))
+            return out
+        finally:
+            patch.uninstall()
+
+    shared = run_once("1")
+    n_shared_calls = len(calls)
+    own = run_once("0")
+    assert len(calls) == n_shared_calls, "DKG_B200_SHARE=0 must not use the shared call"
+    assert n_shared_calls >= 2 and n_shared_calls <= 5, n_shared_calls
+    assert shared == own
+    for partials, plains in shared:
+        assert all(p == ms for p in plains)
+
+
 def _v_inputs(case):
     return ([_h(g) for g in case["g_values"]], _h(case["n"]), [_h(x) for x in case["p_shares"]],
             [_h(x) for x in case["q_shares"]], case["correct_param_biprime"])
