@@ -485,7 +485,7 @@ def secondary_block(peak_tmacs: float) -> list:
     # cfg5: biprimality-test batch sweep, host buffers end to end, party 1 exponent, 40 bases per candidate
     rng = random.Random(5)
     sweep = []
-    for C in (1, 4, 16, 64, 256, 1024, 4096, 16384, 65536):
+    for C in (1, 4, 16, 64, 256, 1024, 4096, 16384, 65536, 131072):
         base_c = min(C, 64)
         moduli, exps = [], []
         for _ in range(base_c):

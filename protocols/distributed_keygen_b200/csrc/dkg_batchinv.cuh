@@ -42,11 +42,13 @@ __global__ void __launch_bounds__(64, 1) batchinv_kernel(const BatchInvParams p)
 
   WarpIO<K, M> ioX;
   ioX.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
+  ioX.ss = ioX.xs;   // (no second operand here: the prefetch's dummy reads go to X)
   ioX.ns = (uint32_t)__cvta_generic_to_shared(Ns);
   ioX.nis = (uint32_t)__cvta_generic_to_shared(NIs);
   ioX.Qg = Qg + lane; ioX.Y = nullptr;
   WarpIO<K, M> ioX2 = ioX;
   ioX2.xs = (uint32_t)__cvta_generic_to_shared(X2w + lane);
+  ioX2.ss = ioX2.xs;
 
   const unsigned long long ngroups = (p.count + 31ull) / 32ull;
   auto group_of = [&](int k) -> unsigned long long { return (unsigned long long)w + (unsigned long long)k * p.nchain_warps; };

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_grouped_kernel(cons
   WarpIO<K, M, true, true> io;
   io.sched_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
   io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
+  io.ss = io.xs;   // (no second operand here: the prefetch's dummy reads go to X)
   io.ns = (uint32_t)__cvta_generic_to_shared(Nw + lane);
   io.nis = (uint32_t)__cvta_generic_to_shared(NIw + lane);
   io.Qg = Qg + lane; io.Y = nullptr;

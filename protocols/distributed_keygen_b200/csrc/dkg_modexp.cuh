@@ -210,7 +210,10 @@ struct WarpIO : XgField<typename VecSel<kpad<K>>::T, XG_> {
     const bool from_shared = xkind && !x_global();
     const bool none = !(xkind || kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2);
     unsigned long long sgen;
-    asm("cvta.shared.u64 %0, %1;" : "=l"(sgen) : "l"((unsigned long long)((none ? ns : xs) + (uint32_t)((none ? 0 : blk) * KV) * 32u * VB)));
+    // (the dummy is block 0 of this lane's own second shared-memory operand -- kernels without one
+    // point ss at X: no other thread writes there)
+    const uint32_t sbase = none ? ss : xs;
+    asm("cvta.shared.u64 %0, %1;" : "=l"(sgen) : "l"((unsigned long long)(sbase + (uint32_t)((none ? 0 : blk) * KV) * 32u * VB)));
     const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : ((xkind && x_global()) ? this->xg_get() : Qg));
     const char* gb = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
     d.base = (from_shared || none) ? reinterpret_cast<const char*>(sgen) : gb;
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_fixed_kernel(const 
 
   WarpIO<K, M> io;
   io.xs = (uint32_t)__cvta_generic_to_shared(Xw + lane);
+  io.ss = io.xs;   // (no second operand here: the prefetch's dummy reads go to X)
   io.ns = (uint32_t)__cvta_generic_to_shared(Ns);
   io.nis = (uint32_t)__cvta_generic_to_shared(NIs);
   io.Qg = Qg + lane; io.Y = nullptr;

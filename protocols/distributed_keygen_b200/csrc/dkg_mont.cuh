@@ -36,7 +36,7 @@ enum MontMode { MONT_MUL = 0, MONT_REDC = 1, MONT_SQR = 2, MONT_MUL2S = 3, MONT_
 // (guarded by io.never(), a run-time condition that is never true) tips the static balance, and every one of those instructions
 // moves to the idle ALU pipe.  It costs code bytes that are never fetched.
 #ifndef DKG_PIPE_BALLAST
-#define DKG_PIPE_BALLAST 3072
+#define DKG_PIPE_BALLAST 4096
 #endif
 DKG_HD uint32_t pipe_ballast(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)

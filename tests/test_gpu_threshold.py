@@ -119,3 +119,37 @@ def test_threshold_context_large_batch_roundtrip(dealer_vectors):
     assert np.array_equal(np.delete(plain, 5, axis=0), np.delete(m_rows[:64], 5, axis=0))
     for key in keys.values():
         key.close()
+
+
+def test_partials_only_call_equals_the_decrypt_call(dealer_vectors):
+    """``dkg_threshold_partials_batch`` (loop 1 of ``_decrypt_sequence_raw`` for every in-process
+    party, ``distributed_keygen.py:463-466``): the same partials as the full decrypt call returns,
+    a status per party, on one device and sharded over all of them, small and large batches."""
+    import protocols.distributed_keygen_b200 as eng
+    from oracle import keys as okeys
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs
+
+    dk = okeys.dealer_key_from_json(dealer_vectors["keys"]["cfg1_k512_p3_t1"]["key"])
+    keys = _gpu_keys(dk.keys)
+    n2 = dk.n * dk.n
+    rng = random.Random(77)
+    exps = {pid: k.partial_decrypt_exponent() for pid, k in dk.keys.items()}
+    for count in (5, 7001):
+        cs = [rng.randrange(1, n2) for _ in range(count)]
+        cs[3] = sum(dk.p_shares) * 4711 % n2        # not a unit: flagged for the parties with a negative exponent only
+        rows = ints_to_limbs(cs, (n2.bit_length() + 31) // 32)
+        for devices in _devices():
+            ctx = dkg.threshold_context(keys, devices)
+            parts, status = ctx.partials_limbs(rows)
+            _, _, want = ctx.decrypt_limbs(rows, want_partials=True)
+            ctx.close()
+            assert status.shape == (ctx.shares, count)
+            for p in range(ctx.shares):
+                neg = exps[p + 1] < 0
+                assert status[p, 3] == (1 if neg else 0) and not np.delete(status[p], 3).any()
+                keep = np.ones(count, dtype=bool)
+                keep[3] = not neg
+                assert np.array_equal(parts[p][keep], want[p][keep])
+    for k in keys.values():
+        k.close()

@@ -61,4 +61,31 @@ for coop in (1, 0):
     assert eng.modexp_grouped(moduli, exps, gs) == [[pow(g, e, m) for g in row] for m, e, row in zip(moduli, exps, gs)]
     eng.small_prime_sieve(moduli, [3, 5, 7, 11])
     eng.jacobi_batch(moduli[:2], gs[:2])
+    if not coop:
+        # round-2 kernels, thread-per-operand route: 13-limb blocks in 14-limb slots (2048-bit N), b
+        # component in global scratch (4096-bit N), the shared squaring chain with a negative party
+        for bits in (2049, 4096):
+            root = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+            m2 = root * root
+            for e in (rng.getrandbits(45), -rng.getrandbits(45)):
+                ctx = eng.ModexpContext(m2, e, root=root)
+                bases = [b for b in (rng.randrange(1, m2) for _ in range(60)) if math.gcd(b, root) == 1][:37]
+                assert ctx.modexp(bases) == [pow(b, e, m2) for b in bases], (bits, e)
+                ctx.close()
+        big = [rng.getrandbits(2050) | 1 | (1 << 2049) for _ in range(2)]
+        bexp = [rng.getrandbits(50) for _ in big]
+        bgs = [[rng.randrange(m) for _ in range(5)] for m in big]
+        assert eng.modexp_grouped(big, bexp, bgs) == [[pow(g, e, m) for g in row] for m, e, row in zip(big, bexp, bgs)]
+        for bits in (130, 2049):
+            root = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+            m2 = root * root
+            exps = {1: rng.getrandbits(60), 2: -rng.getrandbits(61), 3: rng.getrandbits(59)}
+            tctx = eng.ThresholdContext(root, 1, exps, [0])
+            cs = [b for b in (rng.randrange(1, m2) for _ in range(80)) if math.gcd(b, root) == 1][:45]
+            from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+            parts, status = tctx.partials_limbs(ints_to_limbs(cs, tctx.n2_limbs))
+            tctx.close()
+            assert not status.any()
+            for pid, e in exps.items():
+                assert limbs_to_ints(parts[pid - 1]) == [pow(c, e, m2) for c in cs], (bits, pid)
     print("sanitize workload ok, cooperative kernels" if coop else "sanitize workload ok, thread-per-operand kernels", flush=True)
