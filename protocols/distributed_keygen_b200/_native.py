@@ -11,7 +11,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdkg_b200.so")
+# DKG_B200_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("DKG_B200_LIB") or os.path.join(_HERE, "libdkg_b200.so")
 
 DKG_OK = 0
 DKG_ERR_INVALID = 1

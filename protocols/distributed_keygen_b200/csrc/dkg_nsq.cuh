@@ -36,64 +36,16 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<kpad<K>>::T* Bv, cons
   constexpr int VW = VecSel<KP>::VW;
   constexpr int LV = KP * M / VW;
   // odd K: the last limb of every slot is a pad (zero in b, N and Dneg); the carry steps over it
-  // (vector v of a number is vector v % KVB of its block: no division in the loops below, they
-  // count blocks and vectors separately)
-  constexpr int KVB = KP / VW;
-  auto is_pad = [](int q, int k) -> bool { return (K & 1) && q == KVB - 1 && k == VW - 1; };
-  // One pass when the sign of b - m shows in the top limbs (all but 2^-32 of the cases): with
-  // D = (-R mod N) for the lanes where b < m and 0 for the others,
-  //   T = b + ~m + 1 + D = b - m + R + D;
-  // b >= m: T is in [R, 2R), dropping R leaves b - m.  b < m: T = (b - m + R) + D is congruent to
-  // b - m modulo N and below R + N; if it passed R (probability about N / R) N comes off once.
-  {
-    constexpr int top = (M - 1) * KP + K - 1;          // top limb of a number, slot layout
-    const uint32_t bt = reinterpret_cast<const uint32_t*>(Bv + (top / VW) * 32)[top % VW];
-    const uint32_t mt = reinterpret_cast<const uint32_t*>(mq + (size_t)(top / VW) * 32)[top % VW];
-    if (!__any_sync(0xffffffffu, bt == mt)) {
-      const uint32_t mask = bt < mt ? 0xffffffffu : 0u;
-      uint32_t carry = 1;
-      for (int v = 0, q = 0; v < LV; ++v, q = (q + 1 == KVB ? 0 : q + 1)) {
-        uint32_t bb[VW], mm[VW];
-        unpack(Bv[v * 32], bb);
-        unpack(mq[(size_t)v * 32], mm);
-#pragma unroll
-        for (int k = 0; k < VW; ++k) {
-          if (is_pad(q, k)) { bb[k] = 0; continue; }
-          const uint64_t s = (uint64_t)bb[k] + (uint32_t)~mm[k] + (Dneg[v * VW + k] & mask) + carry;
-          bb[k] = (uint32_t)s;
-          carry = (uint32_t)(s >> 32);
-        }
-        V o; pack(o, bb); Bv[v * 32] = o;
-      }
-      const uint32_t over = mask & (0u - (uint32_t)(carry != 0u));
-      if (__any_sync(0xffffffffu, over)) {
-        uint32_t borrow = 0;
-        for (int v = 0, q = 0; v < LV; ++v, q = (q + 1 == KVB ? 0 : q + 1)) {
-          uint32_t bb[VW];
-          unpack(Bv[v * 32], bb);
-#pragma unroll
-          for (int k = 0; k < VW; ++k) {
-            if (is_pad(q, k)) continue;
-            const uint64_t d = (uint64_t)bb[k] - (Ns[v * VW + k] & over) - borrow;
-            bb[k] = (uint32_t)d;
-            borrow = (uint32_t)(d >> 63);
-          }
-          V o; pack(o, bb); Bv[v * 32] = o;
-        }
-      }
-      return;
-    }
-  }
-  // (equal top limbs in some lane: the sign needs the full subtraction)
+  auto is_pad = [](int v, int k) -> bool { return (K & 1) && (v * VW + k) % KP == K; };
   // S = b + (R - m) = b + ~m + 1
   uint32_t carry = 1;
-  for (int v = 0, q = 0; v < LV; ++v, q = (q + 1 == KVB ? 0 : q + 1)) {
+  for (int v = 0; v < LV; ++v) {
     uint32_t bb[VW], mm[VW];
     unpack(Bv[v * 32], bb);
     unpack(mq[(size_t)v * 32], mm);
 #pragma unroll
     for (int k = 0; k < VW; ++k) {
-      if (is_pad(q, k)) { bb[k] = 0; continue; }
+      if (is_pad(v, k)) { bb[k] = 0; continue; }
       const uint64_t s = (uint64_t)bb[k] + (uint32_t)~mm[k] + carry;
       bb[k] = (uint32_t)s;
       carry = (uint32_t)(s >> 32);
@@ -106,12 +58,12 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<kpad<K>>::T* Bv, cons
   if (__any_sync(0xffffffffu, need)) {
     const uint32_t mask = 0u - need;
     uint32_t c2 = 0;
-    for (int v = 0, q = 0; v < LV; ++v, q = (q + 1 == KVB ? 0 : q + 1)) {
+    for (int v = 0; v < LV; ++v) {
       uint32_t bb[VW];
       unpack(Bv[v * 32], bb);
 #pragma unroll
       for (int k = 0; k < VW; ++k) {
-        if (is_pad(q, k)) continue;
+        if (is_pad(v, k)) continue;
         const uint64_t s = (uint64_t)bb[k] + (Dneg[v * VW + k] & mask) + c2;
         bb[k] = (uint32_t)s;
         c2 = (uint32_t)(s >> 32);
@@ -121,12 +73,12 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<kpad<K>>::T* Bv, cons
     if (__any_sync(0xffffffffu, c2)) {
       const uint32_t mask2 = 0u - c2;
       uint32_t borrow = 0;
-      for (int v = 0, q = 0; v < LV; ++v, q = (q + 1 == KVB ? 0 : q + 1)) {
+      for (int v = 0; v < LV; ++v) {
         uint32_t bb[VW];
         unpack(Bv[v * 32], bb);
 #pragma unroll
         for (int k = 0; k < VW; ++k) {
-          if (is_pad(q, k)) continue;
+          if (is_pad(v, k)) continue;
           const uint64_t d = (uint64_t)bb[k] - (Ns[v * VW + k] & mask2) - borrow;
           bb[k] = (uint32_t)d;
           borrow = (uint32_t)(d >> 63);
