@@ -196,7 +196,11 @@ int ensure_scratch(DeviceState* d, size_t words) {
     d->scratch_words = 0;
   }
   cudaError_t e = cudaMalloc(&d->scratch, words * sizeof(uint32_t));
-  if (e != cudaSuccess) return fail(DKG_ERR_NOMEM, std::string("scratch cudaMalloc: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    cudaGetLastError();   // (clear it: callers may fall back to a smaller layout and launch again)
+    d->scratch = nullptr;
+    return fail(DKG_ERR_NOMEM, std::string("scratch cudaMalloc: ") + cudaGetErrorString(e));
+  }
   d->scratch_words = words;
   return DKG_OK;
 }
@@ -1836,6 +1840,12 @@ int run_threshold_shard(dkg_threshold_ctx* t, dkg_threshold_ctx::Dev& dv, const 
           for (int p = 0; p < S; ++p) fused = fused && dv.parties[p]->coop && dv.parties[p]->use_nsq && rows * (size_t)S <= dv.parties[p]->coop_max;
           if (!fused && dv.multi_kernel != nullptr) {
             rc = launch_threshold_multi(dv, S, B.in, B.part, B.st, rows, s);
+            if (rc == DKG_ERR_NOMEM) {   // no room for the bucket scratch: one exponentiation per party from here on
+              dv.multi_kernel = nullptr;
+              rc = DKG_OK;
+              for (int p = 0; p < S && rc == DKG_OK; ++p)
+                rc = launch_modexp(dv.parties[p], B.in, B.part + (size_t)p * rows * l2, B.st + (size_t)p * rows, nullptr, rows, s);
+            }
           } else if (fused) {
             rc = launch_modexp_coop_parties(dv.parties.data(), S, B.in, B.part, B.st, rows, s, nullptr, 0);
             for (int p = 0; p < S && rc == DKG_OK; ++p)
@@ -2033,6 +2043,12 @@ int dkg_threshold_decrypt_batch_device(dkg_threshold_ctx* t, const uint32_t* d_c
   int rc = DKG_OK;
   if (!fused && dv.multi_kernel != nullptr) {
     rc = launch_threshold_multi(dv, S, d_ciphertexts, d_partials, d_status, count, s);
+    if (rc == DKG_ERR_NOMEM) {   // no room for the bucket scratch: one exponentiation per party from here on
+      dv.multi_kernel = nullptr;
+      rc = DKG_OK;
+      for (int p = 0; p < S && rc == DKG_OK; ++p)
+        rc = launch_modexp(dv.parties[p], d_ciphertexts, d_partials + (size_t)p * count * t->l2, d_status + (size_t)p * count, nullptr, count, s);
+    }
   } else if (fused) {
     rc = launch_modexp_coop_parties(dv.parties.data(), S, d_ciphertexts, d_partials, d_status, count, s, nullptr, 0);
     for (int p = 0; p < S && rc == DKG_OK; ++p)
