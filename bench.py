@@ -753,6 +753,33 @@ def main() -> None:
             got = limbs_to_ints(part_host[s, i : i + 1])[0]
             assert got == want, f"rank {rank}: partial decryption mismatch party {pid} element {i}"
     assert int(d_pstatus.max().item()) == 0 and int(d_cstatus.max().item()) == 0
+
+    # ---- the same step WITHOUT the shared squaring chain: one left-to-right exponentiation per party
+    # (each party's own call, what separate processes / machines would run) + the combination; one
+    # untimed and one timed pass, reported next to `value` so that the share of the speed-up that
+    # needs all parties in one process is visible
+    per_party_ms = None
+    if world == 1 and not args.no_secondary:
+        d_parts2 = torch.empty_like(d_partials)
+        d_st2 = torch.empty((shares, B), dtype=torch.uint8, device="cuda")
+        d_plain2 = torch.empty_like(d_plain)
+        d_cst2 = torch.empty(B, dtype=torch.uint8, device="cuda")
+
+        def per_party_step():
+            for s_, pid in enumerate(range(1, shares + 1)):
+                ctxs[pid].modexp_device(d_cts.data_ptr(), d_parts2[s_].data_ptr(), d_st2[s_].data_ptr(), B, stream)
+            comb.combine_device(d_parts2.data_ptr(), d_plain2.data_ptr(), d_cst2.data_ptr(), B, stream)
+
+        per_party_step()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        per_party_step()
+        p1.record()
+        torch.cuda.synchronize()
+        per_party_ms = p0.elapsed_time(p1)
+        assert torch.equal(d_parts2, d_partials) and torch.equal(d_plain2, d_plain), "shared chain and per-party kernels disagree"
+        del d_parts2, d_plain2
     plain_host = d_plain.cpu().numpy().view(np.uint32)
     theta_inv = pow(dk.theta, -1, dk.n)
     for i in (0, B // 2, B - 1):
@@ -853,6 +880,10 @@ def main() -> None:
                 "exponent_bits": [abs(exps[p]).bit_length() * (1 if exps[p] > 0 else -1) for p in sorted(exps)],
                 "kernel_shape": info, "parallelism": f"index-sharded x{world}, no collective",
                 "cache": "inputs+outputs per step (%.0f MB) larger than L2" % ((shares + 1) * B * L2 * 4 / 1e6),
+                "without_shared_squaring_chain": (None if per_party_ms is None else {
+                    "value": B / (per_party_ms * 1e-3), "unit": UNIT, "ms_per_step": per_party_ms,
+                    "note": "one left-to-right exponentiation per party (every party's own call) + combination, same batch, "
+                            "one timed pass; all partials and plaintexts bit-identical to the timed path"}),
             },
             "roofline": {
                 "bound": "imad", "achieved": achieved, "peak": peak, "unit": "T wide-MAC/s",
