@@ -55,38 +55,13 @@ __device__ __forceinline__ void ldg_vec(uint2& v, const uint2* p) {
   asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
 }
 
-// two predicated loads (global / shared); the registers keep their value when both are off
-__device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t on_g, uint32_t sp, uint32_t on_s, uint4) {
-  asm volatile("{\n\t.reg .pred pg, ps;\n\tsetp.ne.u32 pg, %5, 0;\n\tsetp.ne.u32 ps, %7, 0;\n\t"
-               "@pg ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t@ps ld.shared.v4.u32 {%0, %1, %2, %3}, [%6];\n\t}"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(gp), "r"(on_g), "r"(sp), "r"(on_s) : "memory");
-}
-__device__ __forceinline__ void ld_pred2(uint32_t* r, const char* gp, uint32_t on_g, uint32_t sp, uint32_t on_s, uint2) {
-  asm volatile("{\n\t.reg .pred pg, ps;\n\tsetp.ne.u32 pg, %3, 0;\n\tsetp.ne.u32 ps, %5, 0;\n\t"
-               "@pg ld.global.v2.u32 {%0, %1}, [%2];\n\t@ps ld.shared.v2.u32 {%0, %1}, [%4];\n\t}"
-               : "+r"(r[0]), "+r"(r[1]) : "l"(gp), "r"(on_g), "r"(sp), "r"(on_s) : "memory");
-}
-
-// one predicated load through a generic address (shared or global window)
-__device__ __forceinline__ void ld_pred_generic(uint32_t* r, const char* p, uint32_t on, uint4) {
-  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %5, 0;\n\t@pp ld.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : "l"(p), "r"(on) : "memory");
-}
-__device__ __forceinline__ void ld_pred_generic(uint32_t* r, const char* p, uint32_t on, uint2) {
-  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %3, 0;\n\t@pp ld.v2.u32 {%0, %1}, [%2];\n\t}"
-               : "+r"(r[0]), "+r"(r[1]) : "l"(p), "r"(on) : "memory");
-}
-
+// one load through a generic address (shared or global window)
 __device__ __forceinline__ void ld_generic(uint4& v, const char* p) {
   asm volatile("ld.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void ld_generic(uint2& v, const char* p) {
   asm volatile("ld.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
 }
-
-#ifndef DKG_GENERIC_PREFETCH
-#define DKG_GENERIC_PREFETCH 1
-#endif
 
 // IO policy of dkg::mont_mul for one thread of a warp.
 //  xs      shared-space byte address of this lane's vector 0 of X (consecutive vectors of one
@@ -193,7 +168,6 @@ struct WarpIO : XgField<typename VecSel<kpad<K>>::T, XG_> {
   }
   // Prefetch descriptor: the next y operand comes either from shared memory (an X block) or from
   // global memory (table entry / quotient block / the global X of the XG layouts).
-#if DKG_GENERIC_PREFETCH
   // ONE predicated load through a generic address.  With two predicated loads (ld.global / ld.shared,
   // exactly one of them on) into the same registers, ptxas sinks the shared-memory ones to the end of
   // the block product, where each of them -- predicated off or not -- waits on the scoreboard of the
@@ -224,24 +198,6 @@ struct WarpIO : XgField<typename VecSel<kpad<K>>::T, XG_> {
     ld_generic(val, d.base + (size_t)v * 32u * VB);
     unpack(val, &r[v * VW]);
   }
-#else
-  // Two predicated loads, exactly one of which is on, keep the block product branch-free without
-  // going through generic addressing.
-  struct Prefetch { const char* gbase; uint32_t sbase; uint32_t on_g; uint32_t on_s; };
-  __device__ __forceinline__ Prefetch prefetch_desc(int kind, int blk) const {
-    Prefetch d;
-    const bool xkind = kind == PAIR_XX || kind == PAIR_XX2 || kind == PAIR_SX2;   // y = a block of X
-    d.on_s = (xkind && !x_global()) ? 1u : 0u;
-    d.on_g = (kind == PAIR_XY || kind == PAIR_NQ || kind == PAIR_SY2 || (xkind && x_global())) ? 1u : 0u;
-    d.sbase = xs + (uint32_t)(blk * KV) * 32u * VB;
-    const V* g = kind == PAIR_XY ? Y : (kind == PAIR_SY2 ? Y2 : ((xkind && x_global()) ? this->xg_get() : Qg));
-    d.gbase = reinterpret_cast<const char*>(g + (size_t)(blk * KV) * 32);
-    return d;
-  }
-  __device__ __forceinline__ void prefetch_load(const Prefetch& d, int v, uint32_t (&r)[KP]) const {
-    ld_pred2(&r[v * VW], d.gbase + (size_t)v * 32u * VB, d.on_g, d.sbase + (uint32_t)v * 32u * VB, d.on_s, V());
-  }
-#endif
   __device__ __forceinline__ void load_n(int j, uint32_t (&r)[KP]) const {
 #pragma unroll
     for (int q = 0; q < KV; q++) { V v; lds_vec(v, ns + (uint32_t)(j * KV + q) * NSTRIDE); unpack(v, &r[q * VW]); }

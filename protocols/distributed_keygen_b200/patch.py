@@ -91,7 +91,10 @@ def _shared_partials(ref_key: Any, values: Sequence[int]) -> list[int] | None:
         return None
     twin = gpu_key(ref_key)
     n = twin.n
-    _PEERS.setdefault(n, {})[twin.player_id] = weakref.ref(ref_key)
+    try:
+        _PEERS.setdefault(n, {})[twin.player_id] = weakref.ref(ref_key)
+    except TypeError:          # a key class without weak-reference support: no sharing
+        return None
     need = range(1, twin.share.degree + 2)
     live = {i: r() for i, r in _PEERS[n].items()}
     if twin.player_id not in need or any(live.get(i) is None for i in need):
