@@ -332,6 +332,8 @@ struct dkg_modexp_ctx {
   // pair arithmetic modulo N when the modulus is N^2 with known N (dkg_nsq.cuh)
   bool nsq = false;
   bool nsq_bg = false;             // b component in global scratch (wide keys: twice the warps per SM)
+  bool nsq_inv = false;            // negative exponents inverted inside the pair kernels (pair_invert)
+  size_t ninv_slot = 0;            // first spare pair slot of a warp's scratch for that
   Shape nshape{};
   int nLp = 0, nLs = 0, nwarps = 1;   // dense / slot-layout limbs of a pair component
   size_t nsmem = 0, nscratch_per_warp = 0, nscratch_q_offset = 0;
@@ -599,7 +601,8 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   const size_t pair_words = count * (size_t)(2 * Lp);
   const uint32_t* src = d_bases;
   size_t inv_words = 0, inv_off = 0;
-  if (ctx->negative) {
+  const bool inv_in_kernel = ctx->negative && ctx->nsq_inv;
+  if (ctx->negative && !inv_in_kernel) {
     if (ctx->inv_kernel == nullptr || ngroups < 1) return DKG_OK;  // let the direct kernel do it
     const size_t gwords = (size_t)ctx->Lp * 32;
     const int nchain = inversion_chain_warps(d, ctx, ngroups);
@@ -643,6 +646,8 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   dkg::NsqParams q{};
   q.pairs_in = pairs; q.pairs_out = pairs; q.count = count; q.consts = ctx->d_nconsts; q.ops = ctx->d_ops;
   q.nops = ctx->nops; q.tab_entries = ctx->tab_entries; q.table_odd = ctx->table_odd; q.ct_table = ctx->ct_table ? 1 : 0; q.scratch = d->scratch; q.scratch_per_warp = ctx->nscratch_per_warp;
+  q.negative = inv_in_kernel ? 1 : 0; q.status = d_status; q.inv_slot = ctx->ninv_slot;
+  if (d_status) CUDA_TRY(cudaMemsetAsync(d_status, 0, count, stream));
   q.scratch_q_offset = ctx->nscratch_q_offset; q.counter = d->counter;
   {
     KernelTimer kt(d, stream);
@@ -653,7 +658,6 @@ int launch_modexp_nsq(dkg_modexp_ctx* ctx, const uint32_t* d_bases, uint32_t* d_
   dkg::nsq_exit_kernel<<<(unsigned)((count + 63) / 64), 64, 0, stream>>>(x);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(3);
-  if (d_status) CUDA_TRY(cudaMemsetAsync(d_status, 0, count, stream));
   *handled = true;
   return DKG_OK;
 }
@@ -955,10 +959,24 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
     kc.insert(kc.end(), sv.begin(), sv.end());
   }
   for (const dkg_host::Limbs* v : {&r2a, &r2b, &onea, &oneb, &plain1, &zero}) append_lane_replicated(kc, slotted(*v), KP);
+  // pair of 2 with 2N added to its a component (Newton step of pair_invert): (2 onea + 2N, 2 oneb - 2R mod N)
+  {
+    dkg_host::Limbs twoa(Lp, 0);
+    uint64_t carry = 0;
+    for (int i = 0; i < Lp; ++i) { uint64_t t = (uint64_t)onea[i] + N[i] + carry; twoa[i] = (uint32_t)t; carry = t >> 32; }
+    uint32_t c2 = 0;
+    for (int i = 0; i < Lp; ++i) { const uint32_t nc = twoa[i] >> 31; twoa[i] = (twoa[i] << 1) | c2; c2 = nc; }
+    const dkg_host::Limbs b2 = dkg_host::addmod(oneb, oneb, N), rr = dkg_host::addmod(r_mod_n, r_mod_n, N);
+    const dkg_host::Limbs twob = dkg_host::submod(b2, rr, N);
+    for (const dkg_host::Limbs* v : {(const dkg_host::Limbs*)&twoa, &twob}) {
+      const dkg_host::Limbs sv = slotted(*v);
+      kc.insert(kc.end(), sv.begin(), sv.end());
+    }
+  }
   std::vector<uint32_t> ioc;
   for (const dkg_host::Limbs* v : {&N, &r2_mod_n, &ninvpos}) ioc.insert(ioc.end(), v->begin(), v->end());
 
-  const size_t uni = (((size_t)(2 * Ls + KP) * 4 + 15) / 16) * 16 +
+  const size_t uni = (((size_t)(2 * Ls + KP + Lp) * 4 + 15) / 16) * 16 +
                      (((size_t)dkg::sched_total_words_closed(sh.M) * 4 + 15) / 16) * 16;  // consts | schedule table
   size_t per_warp = (size_t)2 * Ls * 32 * 4;
   int maxw = DKG_MAX_THREADS / 32;
@@ -974,8 +992,15 @@ int dkg_modexp_ctx_create_nsq(int device, const uint32_t* n, int n_limbs, const 
     }
   }
   if (warps < 1) return DKG_OK;
-  const size_t tsize = (size_t)ctx->tab_entries + 1;  // odd powers, then the slot of c^2
-  ctx->nscratch_q_offset = std::max<size_t>(tsize, 1) * 2 * (size_t)Ls * 32;
+  // window table (odd powers, then the slot of c^2 / the constant-time spare), then 4 pair slots of
+  // work space for the in-kernel inversion of negative exponents
+  const size_t tsize = (size_t)ctx->tab_entries + 1;
+  ctx->ninv_slot = std::max<size_t>(tsize, 1);
+  // (off by default: measured 0.5 % slower than the batched inversion kernel, whose one GCD per chain
+  // runs beside idle SMs, while these GCDs -- one per ciphertext, divergent -- take the exponentiation
+  // kernel's own time; what it buys is an exact per-element status without the predicated redo)
+  ctx->nsq_inv = env_long("DKG_INKERNEL_INVERSE", 0) != 0;
+  ctx->nscratch_q_offset = (ctx->ninv_slot + 4) * 2 * (size_t)Ls * 32;
   ctx->nscratch_per_warp = ctx->nscratch_q_offset + (size_t)Ls * 32 * (bg ? 2 : 1);   // Q [| b]
   ctx->nsq_bg = bg;
   cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(uni + per_warp * warps));
@@ -1689,8 +1714,15 @@ int launch_threshold_multi(dkg_threshold_ctx::Dev& dv, int S, const uint32_t* d_
   const int Lp = c0->nLp, l2 = c0->limbs;
   const unsigned long long ngroups = (rows + 31) / 32;
   const size_t pair_words = rows * (size_t)(2 * Lp);
+  // negative exponents: the party's RESULTS are inverted inside the kernel (pair_invert, exact
+  // per-element status) or, with DKG_INKERNEL_INVERSE=0, by the batched inversion behind it
+  const bool inv_in_kernel = c0->nsq_inv;
+  unsigned int negative_mask = 0;
   bool any_neg = false;
-  for (int p = 0; p < S; ++p) any_neg = any_neg || dv.parties[p]->negative;
+  for (int p = 0; p < S; ++p) {
+    if (dv.parties[p]->negative && inv_in_kernel) negative_mask |= 1u << p;
+    any_neg = any_neg || (dv.parties[p]->negative && !inv_in_kernel);
+  }
   const size_t gwords = (size_t)c0->Lp * 32;
   const int nchain = inversion_chain_warps(d, c0, ngroups);
   const int chain_len = (int)((ngroups + nchain - 1) / nchain);
@@ -1715,6 +1747,7 @@ int launch_threshold_multi(dkg_threshold_ctx::Dev& dv, int S, const uint32_t* d_
   dkg::NsqMultiParams q{};
   q.pairs_in = pairs_in; q.pairs_out = pairs_out; q.count = rows; q.consts = c0->d_nconsts; q.digits = dv.d_digits;
   q.nparties = S; q.nwin = dv.multi_nwin; q.wbits = dv.multi_w; q.scratch = d->scratch;
+  q.negative_mask = negative_mask; q.status = d_st;
   q.scratch_per_warp = dv.multi_scratch_per_warp; q.scratch_q_offset = dv.multi_q_offset; q.counter = d->counter;
   {
     KernelTimer kt(d, stream);
@@ -1728,7 +1761,7 @@ int launch_threshold_multi(dkg_threshold_ctx::Dev& dv, int S, const uint32_t* d_
   for (int p = 0; p < S; ++p) {
     dkg_modexp_ctx* c = dv.parties[p];
     uint32_t* out_p = d_part + (size_t)p * rows * l2;
-    if (c->negative) {
+    if (c->negative && !inv_in_kernel) {
       dkg::BatchInvParams b{};
       b.bases = out_p; b.count = rows; b.in_limbs = l2; b.consts = c->d_consts; b.n0inv = c->n0inv;
       b.chain_s = inv_area; b.chain_p = inv_area + ngroups * gwords; b.scratch = inv_area + 2 * ngroups * gwords;
@@ -1921,7 +1954,7 @@ int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t
   int best = 0;
   long best_cost = -1;
   for (int w = 1; w <= 8; ++w) {
-    const size_t words = total_warps * (((size_t)shares << w) + 2) * slot_words;
+    const size_t words = total_warps * (((size_t)shares << w) + 2 + 4) * slot_words;
     if (w > 1 && words > cap_words) break;
     const long cost = (ebits + w - 1) / w + 2 * ((1L << w) - 2);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
@@ -1945,7 +1978,7 @@ int setup_threshold_multi(dkg_threshold_ctx::Dev& dv, int shares, const uint32_t
   CUDA_TRY(cudaMalloc(&dv.d_digits, digits.size()));
   CUDA_TRY(cudaMemcpy(dv.d_digits, digits.data(), digits.size(), cudaMemcpyHostToDevice));
   dv.multi_w = w; dv.multi_nwin = nwin;
-  dv.multi_q_offset = (((size_t)shares << w) + 2) * slot_words;
+  dv.multi_q_offset = (((size_t)shares << w) + 2 + 4) * slot_words;   // buckets | parked power | accumulator | inversion work space
   dv.multi_scratch_per_warp = dv.multi_q_offset + (size_t)c0->nLs * 32 * (c0->nsq_bg ? 2 : 1);   // Q [| b]
   dv.multi_kernel = kernel;
   return DKG_OK;

@@ -89,6 +89,77 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<kpad<K>>::T* Bv, cons
   }
 }
 
+// ---- inversion in the pair domain ------------------------------------------------------------------
+// (A, B) <- Montgomery pair of x^-1 from the Montgomery pair of x (negative exponents: the reference
+// inverts with mod_inv, paillier_shared_key.py:89-91).  g = a^-1 mod N by ONE binary GCD on the a
+// component only (half the limbs of N^2: a quarter of the work of inverting modulo N^2), then the
+// pair of y0 = g R -- an inverse of x modulo N -- and one Newton step y0 (2 - x y0) in the pair
+// domain (precision N -> N^2).  Per instance, so the "not invertible" status is exact per element.
+// Integer model with the bounds: tests/test_pair_model.py::pair_inverse.
+//   work: global scratch, 2 La * 32 words (GCD arrays u, v) then 3 pair slots (x, y0, a temporary),
+//   lane offset NOT applied; the other two GCD arrays sit where A and B are (shared or global).
+// Returns 1 if x is not a unit (the pair is then unspecified), else 0.
+template <int K, int M, class PairMul>
+__device__ __forceinline__ uint32_t pair_invert(typename VecSel<kpad<K>>::T* Aw, typename VecSel<kpad<K>>::T* Bw,
+                                                uint32_t* work, const uint32_t* U32, const uint32_t* Nd,
+                                                const uint32_t* two_ab, const typename VecSel<kpad<K>>::T* R2Ar,
+                                                const typename VecSel<kpad<K>>::T* R2Br, int lane, PairMul&& pair_mul) {
+  constexpr int KP = kpad<K>;
+  using V = typename VecSel<KP>::T;
+  constexpr int VW = VecSel<KP>::VW;
+  constexpr int Lp = KP * M, La = K * M, LV = Lp / VW, KVB = KP / VW;
+  uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
+  uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
+  uint32_t* pu = work + lane;
+  uint32_t* pv = pu + La * 32;
+  V* slots = reinterpret_cast<V*>(work + 2 * La * 32 + ((2 * La * 32) % VW ? 1 : 0));
+  auto slot_a = [&](int s) -> V* { return slots + (size_t)s * 2 * LV * 32 + lane; };
+  auto slot_b = [&](int s) -> V* { return slots + ((size_t)s * 2 + 1) * LV * 32 + lane; };
+  auto sidx_of = [&](int l) -> int { const int sl = (l / K) * KP + l % K; return ((sl / VW) * 32 + lane) * VW + sl % VW; };
+  // x -> slot 0; a (dense) -> u
+  for (int v = 0; v < LV; ++v) { slot_a(0)[(size_t)v * 32] = Aw[v * 32 + lane]; slot_b(0)[(size_t)v * 32] = Bw[v * 32 + lane]; }
+  for (int l = 0; l < La; ++l) pu[l * 32] = Aw32[sidx_of(l)];
+  uint32_t bad = 0;
+  const uint32_t* g = mod_inverse_arrays(pu, pv, Aw32 + lane, Bw32 + lane, Nd, U32[Lp], La, &bad);
+  // g sits in one of the four arrays: through u (free by now) into the plain pair (g, 0)
+  if (g != pu) for (int l = 0; l < La; ++l) pu[l * 32] = g[l * 32];
+  {
+    const V zero = V();
+    for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = zero; Bw[v * 32 + lane] = zero; }
+  }
+  for (int l = 0; l < La; ++l) Aw32[sidx_of(l)] = pu[l * 32];
+  pair_mul(R2Ar, R2Br);
+  pair_mul(R2Ar, R2Br);                                   // pair of g R = y0
+  for (int v = 0; v < LV; ++v) { slot_a(1)[(size_t)v * 32] = Aw[v * 32 + lane]; slot_b(1)[(size_t)v * 32] = Bw[v * 32 + lane]; }
+  pair_mul(slot_a(0), slot_b(0));                         // pair of x y0 = 1 (mod N)
+  // (A, B) <- 2 - (A, B):  A <- TWOA - A (no borrow out: TWOA >= 2N > A),  B <- TWOB - B (mod N)
+  const uint32_t* twoa = two_ab;
+  const uint32_t* twob = two_ab + Lp;
+  {
+    uint32_t borrow = 0;
+    for (int v = 0, q = 0; v < LV; ++v, q = (q + 1 == KVB ? 0 : q + 1)) {
+      uint32_t aa[VW], bb[VW], tb[VW];
+      unpack(Aw[v * 32 + lane], aa);
+      unpack(Bw[v * 32 + lane], bb);
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        tb[k] = twob[v * VW + k];
+        if ((K & 1) && q == KVB - 1 && k == VW - 1) { aa[k] = 0; continue; }
+        const uint64_t d = (uint64_t)twoa[v * VW + k] - aa[k] - borrow;
+        aa[k] = (uint32_t)d;
+        borrow = (uint32_t)(d >> 63);
+      }
+      V oa, ob, ot; pack(oa, aa); pack(ob, bb); pack(ot, tb);
+      Aw[v * 32 + lane] = oa;
+      slot_b(2)[(size_t)v * 32] = ob;                     // the old b: what pair_fixup subtracts
+      Bw[v * 32 + lane] = ot;
+    }
+  }
+  pair_fixup<K, M>(Bw + lane, slot_b(2), U32, U32 + Lp + KP);
+  pair_mul(slot_a(1), slot_b(1));                         // y0 (2 - x y0)
+  return bad;
+}
+
 template <int M>
 constexpr int kNsqSchedWords = sched_offset<M>(kSchedModes);
 
@@ -107,15 +178,17 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // N[Lp] | NINV[KP] | DNEG[Lp]  (slot layout)
-  constexpr int UNI0 = ((2 * Lp + KP) * 4 + 15) / 16 * 16;
+  constexpr int UNI0 = ((2 * Lp + KP + La) * 4 + 15) / 16 * 16;   // ... | N once more, dense (the GCD of pair_invert)
   // ... | schedule table (kNsqSchedWords<M> words, see fill_schedule)
   constexpr int UNI = UNI0 + (kNsqSchedWords<M> * 4 + 15) / 16 * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * Lp + KP; i += blockDim.x) U32[i] = p.consts[i];
+  for (int i = threadIdx.x; i < La; i += blockDim.x) U32[2 * Lp + KP + i] = p.consts[(i / K) * KP + i % K];
   fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw + UNI0));
   __syncthreads();
   const uint32_t* Ns32 = U32;
   const uint32_t* Dneg = U32 + Lp + KP;
+  const uint32_t* Nd = U32 + 2 * Lp + KP;
 
   V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * (BG ? 1 : 2) * LV * 32;
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
@@ -126,6 +199,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
   const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
           *ONEBr = Crep + (size_t)3 * LV * 32,
           *PLAIN1r = Crep + (size_t)4 * LV * 32, *ZEROr = Crep + (size_t)5 * LV * 32;
+  const uint32_t* two_ab = p.consts + (2 * Lp + KP) + 6 * Lp + 6 * Lp * 32;   // TWOA | TWOB, slot layout
 
   const unsigned gwarp = blockIdx.x * nwarps + warp;
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
@@ -185,6 +259,9 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
     __syncwarp();
 
     pair_mul(R2Ar, R2Br);   // into the Montgomery domain: value c * R
+    uint32_t st = 0;
+    if (p.negative)
+      st = pair_invert<K, M>(Aw, Bw, scratch32 + p.inv_slot * (unsigned long long)(2 * Lp * 32), U32, Nd, two_ab, R2Ar, R2Br, lane, pair_mul);
     if (p.nops == 0) {
       for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = ONEA[v]; Bw[v * 32 + lane] = ONEB[v]; }
     } else {
@@ -251,6 +328,13 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_kernel(const Ns
       }
     }
     pair_mul(PLAIN1r, ZEROr);   // out of the Montgomery domain: the pair now stands for the result itself
+    if (p.negative) {
+      if (st) {                 // not a unit: zero row, status 1 (what mod_inv's ZeroDivisionError becomes)
+        const V zero = V();
+        for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = zero; Bw[v * 32 + lane] = zero; }
+      }
+      if (p.status != nullptr && lane < cnt) p.status[first + lane] = (uint8_t)st;
+    }
     __syncwarp();
 
     for (int r = 0; r < cnt; ++r) {
@@ -296,14 +380,16 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* U32 = reinterpret_cast<uint32_t*>(smem_raw);   // same uniform area as modexp_nsq_kernel
-  constexpr int UNI0 = ((2 * Lp + KP) * 4 + 15) / 16 * 16;
+  constexpr int UNI0 = ((2 * Lp + KP + La) * 4 + 15) / 16 * 16;   // ... | N once more, dense (the GCD of pair_invert)
   constexpr int UNI = UNI0 + (kNsqSchedWords<M> * 4 + 15) / 16 * 16;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * Lp + KP; i += blockDim.x) U32[i] = p.consts[i];
+  for (int i = threadIdx.x; i < La; i += blockDim.x) U32[2 * Lp + KP + i] = p.consts[(i / K) * KP + i % K];
   fill_schedule<M>(reinterpret_cast<uint32_t*>(smem_raw + UNI0));
   __syncthreads();
   const uint32_t* Ns32 = U32;
   const uint32_t* Dneg = U32 + Lp + KP;
+  const uint32_t* Nd = U32 + 2 * Lp + KP;
 
   V* Aw = reinterpret_cast<V*>(smem_raw + UNI) + (size_t)warp * (BG ? 1 : 2) * LV * 32;
   uint32_t* Aw32 = reinterpret_cast<uint32_t*>(Aw);
@@ -312,6 +398,7 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
   const V* R2Ar = Crep, *R2Br = Crep + (size_t)LV * 32, *ONEAr = Crep + (size_t)2 * LV * 32,
           *ONEBr = Crep + (size_t)3 * LV * 32,
           *PLAIN1r = Crep + (size_t)4 * LV * 32, *ZEROr = Crep + (size_t)5 * LV * 32;
+  const uint32_t* two_ab = p.consts + (2 * Lp + KP) + 6 * Lp + 6 * Lp * 32;   // TWOA | TWOB, slot layout
 
   const unsigned gwarp = blockIdx.x * nwarps + warp;
   uint32_t* scratch32 = p.scratch + (size_t)gwarp * p.scratch_per_warp;
@@ -412,7 +499,19 @@ __global__ void __launch_bounds__(DKG_MAX_THREADS, 1) modexp_nsq_multi_kernel(co
         if (d > 1) fetch(CUR);
       }
       // (D = 2: the single bucket is the result and is already in (A, B); otherwise S is)
+      uint32_t st = 0;
+      const bool neg = (p.negative_mask >> q) & 1u;
+      if (neg)   // (c^-1)^|e| = (c^|e|)^-1: the RESULT is inverted, per instance
+        st = pair_invert<K, M>(Aw, Bw, scratch32 + (unsigned long long)(p.nparties * D + 2) * (unsigned long long)(2 * Lp * 32), U32, Nd,
+                               two_ab, R2Ar, R2Br, lane, pair_mul);
       pair_mul(PLAIN1r, ZEROr);   // out of the Montgomery domain
+      if (neg) {
+        if (st) {
+          const V zero = V();
+          for (int v = 0; v < LV; ++v) { Aw[v * 32 + lane] = zero; Bw[v * 32 + lane] = zero; }
+        }
+        if (p.status != nullptr && lane < cnt) p.status[(size_t)q * p.count + first + lane] = (uint8_t)st;
+      }
       __syncwarp();
       uint32_t* outp = p.pairs_out + (size_t)q * p.count * (size_t)(2 * La);
       for (int r = 0; r < cnt; ++r) {

@@ -70,3 +70,47 @@ def test_full_exponent_4096_bit_key_matches_cpython(wave_route, dealer_vectors):
         got = ctx.modexp(cs)
         ctx.close()
         assert got == [pow(pow(c, -1, n2), -e, n2) if e < 0 else pow(c, e, n2) for c in cs], pid
+
+
+def test_in_kernel_inversion_option(wave_route, monkeypatch, dealer_vectors):
+    """``DKG_INKERNEL_INVERSE=1``: negative exponents inverted inside the pair kernels (pair_invert: GCD on
+    the a component + one Newton step in the pair domain) instead of by the batched inversion kernel:
+    same partials, exact per-element status for non-units, single-party and shared-chain kernels."""
+    import protocols.distributed_keygen_b200 as eng
+    from oracle import keys as okeys
+    from protocols.distributed_keygen_b200 import distributed_keygen as dkg
+    from protocols.distributed_keygen_b200.limbs import ints_to_limbs, limbs_to_ints
+
+    monkeypatch.setenv("DKG_INKERNEL_INVERSE", "1")
+    for name in ("cfg1_k512_p3_t1", "cfg2_k2048_p3_t1_real"):
+        dk = okeys.dealer_key_from_json(dealer_vectors["keys"][name]["key"])
+        n2 = dk.n * dk.n
+        rng = random.Random(len(name))
+        cs = [rng.randrange(1, n2) for _ in range(70)]
+        cs[9] = sum(dk.p_shares) * 31337 % n2          # not a unit
+        rows = ints_to_limbs(cs, (n2.bit_length() + 31) // 32)
+        exps = {pid: k.partial_decrypt_exponent() for pid, k in dk.keys.items()}
+        assert any(e < 0 for e in exps.values())
+        for pid, e in exps.items():
+            ctx = eng.ModexpContext(n2, e, root=dk.n)
+            out, status = ctx.modexp_limbs(rows)
+            ctx.close()
+            if e < 0:
+                assert status[9] == 1 and not out[9].any() and not np.delete(status, 9).any()
+            else:
+                assert not status.any()
+            keep = [i for i in range(len(cs)) if not (e < 0 and i == 9)]
+            assert [limbs_to_ints(out[i : i + 1])[0] for i in keep] == [pow(cs[i], e, n2) for i in keep], (name, pid)
+        keys = {}
+        for pid, k in dk.keys.items():
+            share = eng.IntegerShares(dict(k.share.shares), k.share.degree, k.share.scaling, k.share.number_of_parties)
+            keys[pid] = eng.PaillierSharedKey(k.n, k.t, pid, share, k.theta)
+        tctx = dkg.threshold_context(keys, [0])
+        parts, status = tctx.partials_limbs(rows)
+        tctx.close()
+        for pid, e in exps.items():
+            keep = [i for i in range(len(cs)) if not (e < 0 and i == 9)]
+            assert status[pid - 1, 9] == (1 if e < 0 else 0)
+            assert [limbs_to_ints(parts[pid - 1, i : i + 1])[0] for i in keep] == [pow(cs[i], e, n2) for i in keep], (name, pid)
+        for k in keys.values():
+            k.close()

@@ -85,3 +85,58 @@ def test_pair_arithmetic_equals_pow():
             for c in (0, 1, N, N * N - 1, rng.randrange(N * N)):
                 e = rng.getrandbits(rng.choice([1, 8, 200]))
                 assert modexp_pair(c, e, N, R) == pow(c, e, N * N)
+
+
+def pair_value(a, b, N, R):
+    """The element of Z_{N^2} a Montgomery pair stands for."""
+    N2 = N * N
+    rho = pow(R, -1, N2)
+    return (a + b * N * rho) * rho % N2
+
+
+def pair_inverse(a, b, N, R, Ninv):
+    """Montgomery pair of x^-1 from the Montgomery pair (a, b) of x, the way the kernels do it
+    (csrc/dkg_nsq.cuh, pair_invert): g = a^-1 mod N by a binary GCD on the a component only, the pair
+    of y0 = g R (an inverse of x modulo N), one Newton step y0 (2 - x y0) in the pair domain."""
+    N2 = N * N
+    pR2 = plain_pair(pow(R, 2, N2), N, R)
+    g = pow(a, -1, N)
+    y0 = pair_mul(g, 0, *pR2, N, R, Ninv)
+    y0 = pair_mul(*y0, *pR2, N, R, Ninv)                 # pair of g R: x y0 = 1 (mod N)
+    assert pair_value(*y0, N, R) % N == pow(pair_value(a, b, N, R), -1, N)
+    at, bt = pair_mul(*y0, a, b, N, R, Ninv)             # pair of x y0
+    a2, b2 = plain_pair(2 * R % N2, N, R)                # pair of 2
+    twoa, twob = a2 + 2 * N, (b2 - 2 * R) % N            # the same element with a larger a component
+    ad = twoa - at                                       # > 0; up to 4N: allowed as the x operand of one product
+    bd = fixup(twob, bt, N, R)
+    assert 0 < ad < 4 * N and 0 <= bd < R
+    assert pair_value(ad, bd, N, R) == (2 - pair_value(at, bt, N, R)) % N2
+    # the product with the wide a component: same formulas, bounds checked here
+    c, d = y0
+    t, m = redc_q(ad * c, N, R, Ninv)
+    s, _ = redc_q(ad * d + bd * c, N, R, Ninv)
+    assert t < 2 * N and s < R
+    return t, fixup(s, m, N, R)
+
+
+def test_pair_inverse_newton_step():
+    rng = random.Random(9)
+    for bits in (20, 61, 130, 515, 2048, 2051):
+        limbs = (bits + 3 + 31) // 32
+        R = 1 << (32 * limbs)
+        for _ in range(6):
+            p = rng.getrandbits(bits // 2) | 1 | (1 << (bits // 2 - 1))
+            q = rng.getrandbits(bits - bits // 2) | 1 | (1 << (bits - bits // 2 - 1))
+            N = p * q
+            N2 = N * N
+            Ninv = (-pow(N, -1, R)) % R
+            pR2 = plain_pair(pow(R, 2, N2), N, R)
+            for x in (1, 2, N2 - 1, N + 1, rng.randrange(1, N2), rng.randrange(1, N2)):
+                import math
+                if math.gcd(x, N) != 1:
+                    continue
+                xa, xb = pair_mul(*plain_pair(x, N, R), *pR2, N, R, Ninv)
+                assert pair_value(xa, xb, N, R) == x
+                ya, yb = pair_inverse(xa, xb, N, R, Ninv)
+                assert ya < 2 * N and yb < R
+                assert pair_value(ya, yb, N, R) == pow(x, -1, N2)
