@@ -96,7 +96,7 @@ __device__ __forceinline__ void pair_fixup(typename VecSel<kpad<K>>::T* Bv, cons
 // pair of y0 = g R -- an inverse of x modulo N -- and one Newton step y0 (2 - x y0) in the pair
 // domain (precision N -> N^2).  Per instance, so the "not invertible" status is exact per element.
 // Integer model with the bounds: tests/test_pair_model.py::pair_inverse.
-//   work: global scratch, 2 La * 32 words (GCD arrays u, v) then 3 pair slots (x, y0, a temporary),
+//   work: global scratch, one pair slot (the GCD arrays u, v) then 3 pair slots (x, y0, a temporary),
 //   lane offset NOT applied; the other two GCD arrays sit where A and B are (shared or global).
 // Returns 1 if x is not a unit (the pair is then unspecified), else 0.
 template <int K, int M, class PairMul>
@@ -112,7 +112,7 @@ __device__ __forceinline__ uint32_t pair_invert(typename VecSel<kpad<K>>::T* Aw,
   uint32_t* Bw32 = reinterpret_cast<uint32_t*>(Bw);
   uint32_t* pu = work + lane;
   uint32_t* pv = pu + La * 32;
-  V* slots = reinterpret_cast<V*>(work + 2 * La * 32 + ((2 * La * 32) % VW ? 1 : 0));
+  V* slots = reinterpret_cast<V*>(work + 2 * Lp * 32);   // (one pair slot for u and v: 2 La <= 2 Lp)
   auto slot_a = [&](int s) -> V* { return slots + (size_t)s * 2 * LV * 32 + lane; };
   auto slot_b = [&](int s) -> V* { return slots + ((size_t)s * 2 + 1) * LV * 32 + lane; };
   auto sidx_of = [&](int l) -> int { const int sl = (l / K) * KP + l % K; return ((sl / VW) * 32 + lane) * VW + sl % VW; };
